@@ -1,0 +1,179 @@
+/*
+ * rtrace.h -- C ABI of librtrace_b200.so, the B200 (sm_100a) replacement for the
+ * data-parallel hot path of Byron/rust-tracer.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to
+ * the reference repo).  Conventions: every function returns RT_OK (0) or a
+ * negative rt_status; no exception or unwinding crosses this boundary;
+ * rt_last_error() returns a thread-local message for the last failure.  The
+ * library owns rt_scene and all device memory behind it; the caller owns every
+ * output buffer.  Output pointers may be host memory (pageable or pinned) or
+ * device memory of the scene's GPU -- the library detects which.  A scene is
+ * immutable after creation and bound to the CUDA device that was current when
+ * it was created.  There is NO CPU fallback: without a usable CUDA device every
+ * compute entry point fails with RT_ERR_CUDA.
+ */
+#ifndef RTRACE_B200_H
+#define RTRACE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum rt_status {
+    RT_OK = 0,
+    RT_ERR_INVALID = -1, /* bad argument (the reference would panic: render.rs:265-266, group.rs:59) */
+    RT_ERR_CUDA = -2,    /* CUDA runtime / driver failure, or no device              */
+    RT_ERR_NOMEM = -3,
+    RT_ERR_BUFFER = -4   /* output buffer too small                                  */
+} rt_status;
+
+/* Opaque scene: replaces `Scene` (src/rust/render.rs:138-142) and the
+ * `SphericalGroup` tree it owns (src/rust/group.rs:16-20,86), flattened once
+ * into a pre-order float4 + skip-link array resident in HBM/L2. */
+typedef struct rt_scene rt_scene;
+
+/* Camera.  NULL wherever a camera is accepted == the reference's fixed camera:
+ * origin `scene.eye`, direction normalize(x-W/2,(H-y)-H/2,W) (render.rs:226-243).
+ * A non-NULL camera is an extension (orbit sweep): the camera-space direction is
+ * rotated by the basis before normalisation; the identity basis reproduces the
+ * reference bit for bit. */
+typedef struct rt_camera {
+    float eye[3];
+    float right[3];
+    float up[3];
+    float forward[3];
+} rt_camera;
+
+/* One ray / one closest-hit record: `Ray` (primitive.rs:9-13), `Hit` (primitive.rs:15-19). */
+typedef struct rt_ray { float pos[3]; float dir[3]; } rt_ray;
+typedef struct rt_hit { float distance; float normal[3]; } rt_hit; /* distance = +inf on miss */
+
+/* Per-call statistics (optional out-parameter; may be NULL). */
+typedef struct rt_stats {
+    uint64_t primary_rays; /* W*H*spp^2 of the rendered rows                               */
+    uint64_t shadow_rays;  /* samples with a hit and g<0 (render.rs:194-203); 0 unless counted */
+    double kernel_ms;      /* device time of the traversal kernel(s), CUDA events           */
+    double total_ms;       /* kernel + gather + copy-out, host wall clock                   */
+    uint32_t kernel_launches;
+    uint32_t gpus;
+} rt_stats;
+
+/* Kernel variants (rt_set_variant).  All produce identical bytes. */
+enum {
+    RT_VARIANT_AUTO = 0,  /* the fastest parity-green kernel for the arguments          */
+    RT_VARIANT_LANE = 1,  /* one thread per pixel, per-lane skip-pointer traversal      */
+    RT_VARIANT_WARP = 2,  /* warp-cooperative traversal (ballot/shuffle)                */
+    RT_VARIANT_TILE = 3   /* tile beam-culling + candidate lists                        */
+};
+
+/* ---- library ------------------------------------------------------------ */
+const char *rt_last_error(void);
+const char *rt_version(void);
+/* Number of usable CUDA devices (0 if none); never fails. */
+int rt_device_count(void);
+/* Make `device` the current CUDA device of the calling thread (scenes are created
+ * on the current device). */
+int rt_set_device(int device);
+/* Select the kernel variant used by subsequent render calls on this thread. */
+int rt_set_variant(int variant);
+
+/* ---- scene: replaces Scene::default + SphericalGroup::pyramid -------------- */
+/* render.rs:145-166 + group.rs:28-66: pyramid(level, origin, radius); the light is
+ * normalised exactly as `Vector::normalized` does (vec.rs:93-95).  level must be
+ * > 1 (group.rs:59-60 asserts) and <= 12.  Built on the current CUDA device. */
+int rt_scene_create(uint32_t level, const float origin[3], float radius,
+                    const float light_unnormalised[3], const float eye[3], rt_scene **out);
+/* Scene::default(): level 8, origin (0,-1,0), radius 1, light (-1,-3,2), eye (0,0,-4). */
+int rt_scene_create_default(rt_scene **out);
+/* An arbitrary group tree in pre-order: spheres4 = n x {cx,cy,cz,r}; skip[i] > i+1
+ * marks node i as a group bound whose subtree ends before skip[i]; leaves have
+ * skip[i] == i+1; node 0 must be a group with skip[0] == n.  Mirrors hand-built
+ * groups such as the reference's test fixture (group.rs:118-151). */
+int rt_scene_create_from_nodes(uint32_t n, const float *spheres4, const uint32_t *skip,
+                               const float light[3], const float eye[3], rt_scene **out);
+void rt_scene_destroy(rt_scene *s);
+/* group.rs:95-109 `count()` -> (groups, items); pins group.rs:183 (5461, 21845). */
+int rt_scene_counts(const rt_scene *s, uint64_t *groups, uint64_t *items);
+/* Copy the flattened scene back to the host (n x float4, n x u32); returns the node
+ * count through n_out; pointers may be NULL to query the size only. */
+int rt_scene_export_nodes(const rt_scene *s, float *spheres4, uint32_t *skip, uint32_t cap, uint32_t *n_out);
+/* The same flattening WITHOUT a device (host logic only; used by tools and the CPU
+ * test-suite): pyramid(level, origin, radius) -> n x float4 + n x u32.  Pass NULL
+ * arrays to query n. */
+int rt_flatten_pyramid_host(uint32_t level, const float origin[3], float radius,
+                            float *spheres4, uint32_t *skip, uint32_t cap, uint32_t *n_out);
+int rt_scene_light(const rt_scene *s, float light[3]);
+int rt_scene_eye(const rt_scene *s, float eye[3]);
+int rt_scene_device(const rt_scene *s);
+
+/* ---- the hot path ---------------------------------------------------------- */
+/* Replaces Renderer::render_region (render.rs:218-255) for the region
+ * [l,r) x [b,t) of a width x height image (b = upper image row, as in
+ * ImageRegion, render.rs:43-72).  Writes (r-l)*(t-b)*4 bytes RGBA8 row-major from
+ * row b (RGBABuffer layout, render.rs:69-71,92-109).  Unlike Renderer::render
+ * (render.rs:264-266) sizes need not be multiples of 64. */
+int rt_render_region(const rt_scene *s, uint16_t width, uint16_t height, uint16_t spp,
+                     uint16_t l, uint16_t b, uint16_t r, uint16_t t,
+                     uint8_t *rgba_out, size_t rgba_len);
+
+/* Replaces the bucket loop of Renderer::render (render.rs:268-309) for one GPU's
+ * share of a frame: rows row_start, row_start+row_stride, ... (row_count of them),
+ * all columns, packed densely with the given pitch in bytes (0 = width*4).
+ * `stream` is a cudaStream_t (NULL = default stream); with a device output pointer
+ * the call is asynchronous on that stream.  camera may be NULL.  kinds_out
+ * (optional, device or host) receives one byte per sample (index ssx*spp+ssy):
+ * 0 background, 1 hit facing away from the light, 2 lit, 3 shadowed. */
+int rt_render_rows(const rt_scene *s, const rt_camera *camera,
+                   uint32_t width, uint32_t height, uint32_t spp,
+                   uint32_t row_start, uint32_t row_stride, uint32_t row_count,
+                   uint8_t *rgba_out, size_t pitch_bytes, uint8_t *kinds_out,
+                   void *stream, rt_stats *stats);
+
+/* Whole frame to a host or device buffer of width*height*4 bytes on the scene's GPU. */
+int rt_render_frame(const rt_scene *s, const rt_camera *camera,
+                    uint32_t width, uint32_t height, uint32_t spp,
+                    uint8_t *rgba_out, size_t rgba_len, rt_stats *stats);
+
+/* Whole frame on ngpu GPUs of this process (devices 0..ngpu-1): the scene is
+ * replicated, rows are interleaved (GPU g renders rows g, g+ngpu, ...) and the
+ * bands are gathered into GPU 0's frame by strided peer copies over NVLink, then
+ * copied to rgba_out (host).  scenes[g] must live on device g.  Replaces the
+ * thread pool + sync_channel of Renderer::render (render.rs:271-307). */
+int rt_render_frame_multi(rt_scene *const *scenes, int ngpu, const rt_camera *camera,
+                          uint32_t width, uint32_t height, uint32_t spp,
+                          uint8_t *rgba_out, size_t rgba_len, rt_stats *stats);
+
+/* Count rays the way the reference's work is counted: primary =
+ * rows*width*spp^2, shadow = samples with a hit facing the light. */
+int rt_count_rays(const rt_scene *s, const rt_camera *camera,
+                  uint32_t width, uint32_t height, uint32_t spp,
+                  uint32_t row_start, uint32_t row_stride, uint32_t row_count,
+                  uint64_t *primary, uint64_t *shadow);
+
+/* Closest-hit traversal of arbitrary rays: TypedGroup::intersect (group.rs:72-83)
+ * + Sphere::intersect (primitive.rs:77-84) starting from Hit::missed().  rays and
+ * hits are host arrays of n elements. */
+int rt_trace_rays(const rt_scene *s, size_t n, const rt_ray *rays, rt_hit *hits);
+
+/* Sustained FP32 FFMA throughput of the scene's device in TFLOP/s, measured with
+ * a register-resident FMA chain on every SM (the roofline denominator). */
+int rt_measure_fp32_peak(int device, double *tflops, double *sm_clock_mhz);
+/* Diagnostics: mode 0 = FFMA chains, mode 1 = alternating FMUL/FADD chains (the
+ * unfused mix the parity rule forces on the discriminant); TFLOP/s counted as 2
+ * flop per FFMA and 1 per FMUL/FADD. */
+int rt_microbench_fp32(int device, int mode, double *tflops);
+
+/* Pinned host memory for output buffers (what the CLI hands to rt_render_frame so
+ * the device-to-host copy runs at full PCIe rate).  Replaces the Vec<u8> of
+ * RGBABuffer::new (render.rs:80-85). */
+int rt_host_alloc(size_t bytes, void **out);
+void rt_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

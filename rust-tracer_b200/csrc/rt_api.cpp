@@ -1,0 +1,616 @@
+// rt_api.cpp -- the C ABI (include/rtrace.h) over the CUDA kernels.
+//
+// No torch types, no exceptions across the boundary, no CPU fallback: every
+// compute entry point needs a CUDA device and fails with RT_ERR_CUDA otherwise.
+#include "../../include/rtrace.h"
+
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "rt_device.cuh"
+#include "rt_kernels.h"
+#include "rt_scene.h"
+
+// ---------------------------------------------------------------------------
+// rt_scene
+// ---------------------------------------------------------------------------
+struct rt_scene {
+    int device = 0;
+    rt::FlatScene flat;
+    uint32_t n = 0;
+    float4 *d_sph = nullptr;
+    uint32_t *d_skip = nullptr;
+    // scratch, guarded by mu (a scene may be used from several host threads)
+    std::mutex mu;
+    uint8_t *d_fb = nullptr;
+    size_t d_fb_cap = 0;
+    uint8_t *d_kinds = nullptr;
+    size_t d_kinds_cap = 0;
+    uint8_t *d_frame = nullptr;  // gathered frame (multi-GPU root)
+    size_t d_frame_cap = 0;
+    unsigned long long *d_ctr = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t own_stream = nullptr;
+};
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local int g_variant = RT_VARIANT_AUTO;
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t e_ = (expr);                                                             \
+        if (e_ != cudaSuccess) return fail(RT_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        ok = (prev == dev) || cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+int kernel_variant() {
+    switch (g_variant) {
+        case RT_VARIANT_LANE:
+            return RT_KERNEL_LANE;
+        default:
+            return RT_KERNEL_WARP;
+    }
+}
+
+// true if ptr is device memory; *dev receives its device ordinal
+bool is_device_ptr(const void *ptr, int *dev) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) {
+        if (dev) *dev = a.device;
+        return true;
+    }
+    return false;
+}
+
+int upload(rt_scene *s) {
+    s->n = (uint32_t)s->flat.skip.size();
+    CUDA_TRY(cudaGetDevice(&s->device));
+    CUDA_TRY(cudaMalloc(&s->d_sph, sizeof(float4) * s->n));
+    CUDA_TRY(cudaMalloc(&s->d_skip, sizeof(uint32_t) * s->n));
+    CUDA_TRY(cudaMemcpy(s->d_sph, s->flat.sph.data(), sizeof(float4) * s->n, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(s->d_skip, s->flat.skip.data(), sizeof(uint32_t) * s->n, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&s->d_ctr, sizeof(unsigned long long) * 2));
+    CUDA_TRY(cudaEventCreate(&s->ev0));
+    CUDA_TRY(cudaEventCreate(&s->ev1));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+    return RT_OK;
+}
+
+int ensure(uint8_t **buf, size_t *cap, size_t need) {
+    if (*cap >= need) return RT_OK;
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr;
+    *cap = 0;
+    cudaError_t e = cudaMalloc(buf, need);
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? RT_ERR_NOMEM : RT_ERR_CUDA, "cudaMalloc(%zu): %s", need, cudaGetErrorString(e));
+    *cap = need;
+    return RT_OK;
+}
+
+void fill_params(const rt_scene *s, const rt_camera *cam, uint32_t w, uint32_t h, uint32_t spp, uint32_t row_start,
+                 uint32_t row_stride, uint32_t row_count, rt::RenderParams &p) {
+    memset(&p, 0, sizeof(p));
+    p.sph = s->d_sph;
+    p.skip = s->d_skip;
+    p.n_nodes = s->n;
+    const float *eye = cam ? cam->eye : s->flat.eye;
+    for (int k = 0; k < 3; k++) {
+        p.eye[k] = eye[k];
+        p.light[k] = s->flat.light[k];
+    }
+    if (cam) {
+        p.has_basis = 1;
+        for (int k = 0; k < 3; k++) {
+            p.basis[k] = cam->right[k];
+            p.basis[3 + k] = cam->up[k];
+            p.basis[6 + k] = cam->forward[k];
+        }
+    }
+    p.width = w;
+    p.height = h;
+    p.spp = spp;
+    p.row_start = row_start;
+    p.row_stride = row_stride;
+    p.row_count = row_count;
+}
+
+int check_frame_args(const rt_scene *s, uint32_t w, uint32_t h, uint32_t spp, uint32_t row_start, uint32_t row_stride,
+                     uint32_t row_count) {
+    if (!s) return fail(RT_ERR_INVALID, "scene is NULL");
+    // RenderOptions fields are u16 (render.rs:34-38)
+    if (w == 0 || h == 0 || w > 65535u || h > 65535u || spp > 65535u)
+        return fail(RT_ERR_INVALID, "width/height must be in 1..65535 and samples-per-pixel in 0..65535 (got %u x %u, spp %u)", w, h, spp);
+    if (row_stride == 0) return fail(RT_ERR_INVALID, "row_stride must be >= 1");
+    if (row_count > 0 && (uint64_t)row_start + (uint64_t)(row_count - 1) * row_stride >= h)
+        return fail(RT_ERR_INVALID, "rows %u + k*%u (k < %u) leave the %u-row image", row_start, row_stride, row_count, h);
+    return RT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *rt_last_error(void) { return g_err; }
+const char *rt_version(void) { return "rtrace-b200 0.2.0 (sm_100a)"; }
+
+int rt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int rt_set_device(int device) {
+    if (device < 0 || device >= rt_device_count()) return fail(RT_ERR_CUDA, "no CUDA device %d (have %d)", device, rt_device_count());
+    CUDA_TRY(cudaSetDevice(device));
+    return RT_OK;
+}
+
+int rt_set_variant(int variant) {
+    if (variant < RT_VARIANT_AUTO || variant > RT_VARIANT_TILE) return fail(RT_ERR_INVALID, "unknown variant %d", variant);
+    g_variant = variant;
+    return RT_OK;
+}
+
+int rt_scene_create(uint32_t level, const float origin[3], float radius, const float light_unnormalised[3],
+                    const float eye[3], rt_scene **out) {
+    if (!out || !origin || !light_unnormalised || !eye) return fail(RT_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    // group.rs:59-60: "Levels equal or smaller than one cause empty groups"
+    if (level <= 1 || level > 12) return fail(RT_ERR_INVALID, "level must be in 2..12 (got %u)", level);
+    if (rt_device_count() == 0) return fail(RT_ERR_CUDA, "no CUDA device: librtrace_b200 has no CPU path");
+    rt_scene *s = new (std::nothrow) rt_scene();
+    if (!s) return fail(RT_ERR_NOMEM, "out of host memory");
+    rt::flatten_pyramid(level, origin, radius, s->flat);
+    rt::normalize3(light_unnormalised, s->flat.light);
+    memcpy(s->flat.eye, eye, sizeof(float) * 3);
+    int rc = upload(s);
+    if (rc != RT_OK) {
+        rt_scene_destroy(s);
+        return rc;
+    }
+    *out = s;
+    return RT_OK;
+}
+
+int rt_scene_create_default(rt_scene **out) {
+    const float origin[3] = {0.0f, -1.0f, 0.0f};  // render.rs:148-152
+    const float light[3] = {-1.0f, -3.0f, 2.0f};  // render.rs:154-158
+    const float eye[3] = {0.0f, 0.0f, -4.0f};     // render.rs:160-164
+    return rt_scene_create(8, origin, 1.0f, light, eye, out);
+}
+
+int rt_scene_create_from_nodes(uint32_t n, const float *spheres4, const uint32_t *skip, const float light[3],
+                               const float eye[3], rt_scene **out) {
+    if (!out || !spheres4 || !skip || !light || !eye) return fail(RT_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    uint64_t g = 0, it = 0;
+    const char *why = "";
+    if (!rt::validate_nodes(n, skip, &g, &it, &why)) return fail(RT_ERR_INVALID, "%s", why);
+    if (rt_device_count() == 0) return fail(RT_ERR_CUDA, "no CUDA device: librtrace_b200 has no CPU path");
+    rt_scene *s = new (std::nothrow) rt_scene();
+    if (!s) return fail(RT_ERR_NOMEM, "out of host memory");
+    s->flat.sph.assign(spheres4, spheres4 + (size_t)n * 4);
+    s->flat.skip.assign(skip, skip + n);
+    s->flat.groups = g;
+    s->flat.items = it;
+    memcpy(s->flat.light, light, sizeof(float) * 3);
+    memcpy(s->flat.eye, eye, sizeof(float) * 3);
+    int rc = upload(s);
+    if (rc != RT_OK) {
+        rt_scene_destroy(s);
+        return rc;
+    }
+    *out = s;
+    return RT_OK;
+}
+
+void rt_scene_destroy(rt_scene *s) {
+    if (!s) return;
+    {
+        DeviceGuard g(s->device);
+        if (s->d_sph) cudaFree(s->d_sph);
+        if (s->d_skip) cudaFree(s->d_skip);
+        if (s->d_fb) cudaFree(s->d_fb);
+        if (s->d_kinds) cudaFree(s->d_kinds);
+        if (s->d_frame) cudaFree(s->d_frame);
+        if (s->d_ctr) cudaFree(s->d_ctr);
+        if (s->ev0) cudaEventDestroy(s->ev0);
+        if (s->ev1) cudaEventDestroy(s->ev1);
+        if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    }
+    delete s;
+}
+
+int rt_scene_counts(const rt_scene *s, uint64_t *groups, uint64_t *items) {
+    if (!s || !groups || !items) return fail(RT_ERR_INVALID, "NULL argument");
+    *groups = s->flat.groups;
+    *items = s->flat.items;
+    return RT_OK;
+}
+
+int rt_scene_export_nodes(const rt_scene *s, float *spheres4, uint32_t *skip, uint32_t cap, uint32_t *n_out) {
+    if (!s) return fail(RT_ERR_INVALID, "scene is NULL");
+    if (n_out) *n_out = s->n;
+    if (!spheres4 && !skip) return RT_OK;
+    if (cap < s->n) return fail(RT_ERR_BUFFER, "need room for %u nodes, got %u", s->n, cap);
+    // read back from the device: this is what the kernels traverse
+    DeviceGuard g(s->device);
+    if (spheres4) CUDA_TRY(cudaMemcpy(spheres4, s->d_sph, sizeof(float4) * s->n, cudaMemcpyDeviceToHost));
+    if (skip) CUDA_TRY(cudaMemcpy(skip, s->d_skip, sizeof(uint32_t) * s->n, cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+int rt_flatten_pyramid_host(uint32_t level, const float origin[3], float radius, float *spheres4, uint32_t *skip,
+                            uint32_t cap, uint32_t *n_out) {
+    if (!origin) return fail(RT_ERR_INVALID, "NULL argument");
+    if (level <= 1 || level > 12) return fail(RT_ERR_INVALID, "level must be in 2..12 (got %u)", level);
+    const uint32_t n = (uint32_t)rt::pyramid_subtree_nodes(level);
+    if (n_out) *n_out = n;
+    if (!spheres4 && !skip) return RT_OK;
+    if (cap < n) return fail(RT_ERR_BUFFER, "need room for %u nodes, got %u", n, cap);
+    rt::FlatScene f;
+    rt::flatten_pyramid(level, origin, radius, f);
+    if (spheres4) memcpy(spheres4, f.sph.data(), sizeof(float) * 4 * n);
+    if (skip) memcpy(skip, f.skip.data(), sizeof(uint32_t) * n);
+    return RT_OK;
+}
+
+int rt_scene_light(const rt_scene *s, float light[3]) {
+    if (!s || !light) return fail(RT_ERR_INVALID, "NULL argument");
+    memcpy(light, s->flat.light, sizeof(float) * 3);
+    return RT_OK;
+}
+
+int rt_scene_eye(const rt_scene *s, float eye[3]) {
+    if (!s || !eye) return fail(RT_ERR_INVALID, "NULL argument");
+    memcpy(eye, s->flat.eye, sizeof(float) * 3);
+    return RT_OK;
+}
+
+int rt_scene_device(const rt_scene *s) { return s ? s->device : fail(RT_ERR_INVALID, "scene is NULL"); }
+
+// ---------------------------------------------------------------------------
+// hot path
+// ---------------------------------------------------------------------------
+static int render_rows_impl(rt_scene *s, const rt_camera *camera, uint32_t width, uint32_t height, uint32_t spp,
+                            uint32_t row_start, uint32_t row_stride, uint32_t row_count, uint8_t *rgba_out,
+                            size_t pitch_bytes, uint8_t *kinds_out, cudaStream_t stream, rt_stats *stats,
+                            uint64_t *count_hits, uint64_t *count_shadow) {
+    int rc = check_frame_args(s, width, height, spp, row_start, row_stride, row_count);
+    if (rc != RT_OK) return rc;
+    const bool counting = count_shadow != nullptr;
+    if (!rgba_out && !counting) return fail(RT_ERR_INVALID, "rgba_out is NULL");
+    const size_t row_bytes = (size_t)width * 4;
+    if (pitch_bytes == 0) pitch_bytes = row_bytes;
+    if (pitch_bytes < row_bytes || (pitch_bytes & 3)) return fail(RT_ERR_INVALID, "pitch %zu too small or not a multiple of 4", pitch_bytes);
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (row_count == 0) return RT_OK;
+
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(RT_ERR_CUDA, "cannot select device %d", s->device);
+    const double t0 = now_ms();
+
+    int out_dev = -1;
+    const bool out_on_device = rgba_out && is_device_ptr(rgba_out, &out_dev);
+    if (out_on_device && out_dev != s->device)
+        return fail(RT_ERR_INVALID, "rgba_out lives on device %d, the scene on device %d", out_dev, s->device);
+    if (out_on_device && (((uintptr_t)rgba_out) & 3)) return fail(RT_ERR_INVALID, "device rgba_out must be 4-byte aligned");
+    int kinds_dev = -1;
+    const bool kinds_on_device = kinds_out && is_device_ptr(kinds_out, &kinds_dev);
+    const size_t kinds_bytes = (size_t)width * row_count * spp * spp;
+
+    const bool need_lock = !out_on_device || (kinds_out && !kinds_on_device) || counting || stats;
+    std::unique_lock<std::mutex> lock(s->mu, std::defer_lock);
+    if (need_lock) lock.lock();
+
+    rt::RenderParams p;
+    fill_params(s, camera, width, height, spp, row_start, row_stride, row_count, p);
+    if (out_on_device) {
+        p.out = rgba_out;
+        p.pitch = pitch_bytes;
+    } else {
+        rc = ensure(&s->d_fb, &s->d_fb_cap, row_bytes * row_count);
+        if (rc != RT_OK) return rc;
+        p.out = s->d_fb;
+        p.pitch = row_bytes;
+    }
+    bool diag = false;
+    if (kinds_out) {
+        diag = true;
+        if (kinds_on_device) {
+            p.kinds = kinds_out;
+        } else {
+            rc = ensure(&s->d_kinds, &s->d_kinds_cap, kinds_bytes ? kinds_bytes : 1);
+            if (rc != RT_OK) return rc;
+            p.kinds = s->d_kinds;
+        }
+    }
+    if (counting) {
+        diag = true;
+        p.ray_counters = s->d_ctr;
+        CUDA_TRY(cudaMemsetAsync(s->d_ctr, 0, sizeof(unsigned long long) * 2, stream));
+    }
+
+    if (stats) CUDA_TRY(cudaEventRecord(s->ev0, stream));
+    CUDA_TRY(rt_launch_render(kernel_variant(), diag, p, stream));
+    if (stats) CUDA_TRY(cudaEventRecord(s->ev1, stream));
+
+    bool must_sync = false;
+    if (!out_on_device && rgba_out) {
+        CUDA_TRY(cudaMemcpy2DAsync(rgba_out, pitch_bytes, s->d_fb, row_bytes, row_bytes, row_count, cudaMemcpyDeviceToHost, stream));
+        must_sync = true;
+    }
+    if (kinds_out && !kinds_on_device && kinds_bytes) {
+        CUDA_TRY(cudaMemcpyAsync(kinds_out, s->d_kinds, kinds_bytes, cudaMemcpyDeviceToHost, stream));
+        must_sync = true;
+    }
+    unsigned long long ctr[2] = {0, 0};
+    if (counting) {
+        CUDA_TRY(cudaMemcpyAsync(ctr, s->d_ctr, sizeof(ctr), cudaMemcpyDeviceToHost, stream));
+        must_sync = true;
+    }
+    if (must_sync || stats) CUDA_TRY(cudaStreamSynchronize(stream));
+    if (counting) {
+        if (count_hits) *count_hits = ctr[0];
+        *count_shadow = ctr[1];
+    }
+    if (stats) {
+        float ms = 0.0f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        stats->kernel_ms = ms;
+        stats->total_ms = now_ms() - t0;
+        stats->primary_rays = (uint64_t)width * row_count * spp * spp;
+        stats->shadow_rays = counting ? ctr[1] : 0;
+        stats->kernel_launches = 1;
+        stats->gpus = 1;
+    }
+    return RT_OK;
+}
+
+int rt_render_rows(const rt_scene *s, const rt_camera *camera, uint32_t width, uint32_t height, uint32_t spp,
+                   uint32_t row_start, uint32_t row_stride, uint32_t row_count, uint8_t *rgba_out, size_t pitch_bytes,
+                   uint8_t *kinds_out, void *stream, rt_stats *stats) {
+    return render_rows_impl(const_cast<rt_scene *>(s), camera, width, height, spp, row_start, row_stride, row_count,
+                            rgba_out, pitch_bytes, kinds_out, (cudaStream_t)stream, stats, nullptr, nullptr);
+}
+
+int rt_render_region(const rt_scene *s, uint16_t width, uint16_t height, uint16_t spp, uint16_t l, uint16_t b,
+                     uint16_t r, uint16_t t, uint8_t *rgba_out, size_t rgba_len) {
+    if (!s) return fail(RT_ERR_INVALID, "scene is NULL");
+    // ImageRegion (render.rs:43-72): l <= r <= width, b <= t <= height
+    if (l > r || b > t || r > width || t > height)
+        return fail(RT_ERR_INVALID, "region [%u,%u)x[%u,%u) is not inside the %ux%u image", l, r, b, t, width, height);
+    const uint32_t rw = r - l, rh = t - b;
+    if (rgba_len < (size_t)rw * rh * 4) return fail(RT_ERR_BUFFER, "rgba_out holds %zu bytes, region needs %zu", rgba_len, (size_t)rw * rh * 4);
+    if (rw == 0 || rh == 0) return RT_OK;
+    if (l == 0 && r == width)
+        return render_rows_impl(const_cast<rt_scene *>(s), nullptr, width, height, spp, b, 1, rh, rgba_out, 0, nullptr,
+                                nullptr, nullptr, nullptr, nullptr);
+    // A column sub-range: render the full rows on the device and copy out the window.
+    rt_scene *ms = const_cast<rt_scene *>(s);
+    DeviceGuard guard(ms->device);
+    uint8_t *rows = nullptr;
+    CUDA_TRY(cudaMalloc(&rows, (size_t)width * rh * 4));
+    int rc = render_rows_impl(ms, nullptr, width, height, spp, b, 1, rh, rows, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (rc == RT_OK) {
+        cudaError_t e = cudaMemcpy2D(rgba_out, (size_t)rw * 4, rows + (size_t)l * 4, (size_t)width * 4, (size_t)rw * 4, rh, cudaMemcpyDefault);
+        if (e != cudaSuccess) rc = fail(RT_ERR_CUDA, "cudaMemcpy2D: %s", cudaGetErrorString(e));
+    }
+    cudaFree(rows);
+    return rc;
+}
+
+int rt_render_frame(const rt_scene *s, const rt_camera *camera, uint32_t width, uint32_t height, uint32_t spp,
+                    uint8_t *rgba_out, size_t rgba_len, rt_stats *stats) {
+    if (rgba_len < (size_t)width * height * 4) return fail(RT_ERR_BUFFER, "rgba_out holds %zu bytes, frame needs %zu", rgba_len, (size_t)width * height * 4);
+    return render_rows_impl(const_cast<rt_scene *>(s), camera, width, height, spp, 0, 1, height, rgba_out, 0, nullptr,
+                            nullptr, stats, nullptr, nullptr);
+}
+
+int rt_render_frame_multi(rt_scene *const *scenes, int ngpu, const rt_camera *camera, uint32_t width, uint32_t height,
+                          uint32_t spp, uint8_t *rgba_out, size_t rgba_len, rt_stats *stats) {
+    if (!scenes || ngpu < 1) return fail(RT_ERR_INVALID, "need at least one scene");
+    if (!rgba_out) return fail(RT_ERR_INVALID, "rgba_out is NULL");
+    if (rgba_len < (size_t)width * height * 4) return fail(RT_ERR_BUFFER, "rgba_out holds %zu bytes, frame needs %zu", rgba_len, (size_t)width * height * 4);
+    for (int g = 0; g < ngpu; g++) {
+        int rc = check_frame_args(scenes[g], width, height, spp, 0, 1, height);
+        if (rc != RT_OK) return rc;
+    }
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (ngpu == 1) return rt_render_frame(scenes[0], camera, width, height, spp, rgba_out, rgba_len, stats);
+
+    const double t0 = now_ms();
+    const size_t row_bytes = (size_t)width * 4;
+    rt_scene *root = scenes[0];
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (int g = 0; g < ngpu; g++) locks.emplace_back(scenes[g]->mu);
+
+    // The gathered frame lives on GPU 0; GPU 0's own band is rendered straight into it.
+    {
+        DeviceGuard guard(root->device);
+        int rc = ensure(&root->d_frame, &root->d_frame_cap, row_bytes * height);
+        if (rc != RT_OK) return rc;
+    }
+    uint8_t *frame = root->d_frame;
+    for (int g = 0; g < ngpu; g++) {
+        rt_scene *s = scenes[g];
+        DeviceGuard guard(s->device);
+        if (!guard.ok) return fail(RT_ERR_CUDA, "cannot select device %d", s->device);
+        if (g > 0) {
+            int can = 0;
+            CUDA_TRY(cudaDeviceCanAccessPeer(&can, root->device, s->device));
+            if (can) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(root->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(RT_ERR_CUDA, "enable peer %d->%d: %s", s->device, root->device, cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+        }
+        const uint32_t rows = (height > (uint32_t)g) ? (height - g + ngpu - 1) / ngpu : 0;
+        if (rows == 0) continue;
+        rt::RenderParams p;
+        fill_params(s, camera, width, height, spp, (uint32_t)g, (uint32_t)ngpu, rows, p);
+        if (g == 0) {
+            p.out = frame;  // rows 0, G, 2G, ... in place
+            p.pitch = row_bytes * ngpu;
+        } else {
+            int rc = ensure(&s->d_fb, &s->d_fb_cap, row_bytes * rows);
+            if (rc != RT_OK) return rc;
+            p.out = s->d_fb;
+            p.pitch = row_bytes;
+        }
+        if (stats) CUDA_TRY(cudaEventRecord(s->ev0, s->own_stream));
+        CUDA_TRY(rt_launch_render(kernel_variant(), false, p, s->own_stream));
+        if (stats) CUDA_TRY(cudaEventRecord(s->ev1, s->own_stream));
+        if (g > 0)  // strided peer copy over NVLink: the pitch de-interleaves the band into the frame
+            CUDA_TRY(cudaMemcpy2DAsync(frame + row_bytes * g, row_bytes * ngpu, s->d_fb, row_bytes, row_bytes, rows, cudaMemcpyDefault, s->own_stream));
+    }
+    double kmax = 0.0;
+    for (int g = ngpu - 1; g >= 0; g--) {
+        rt_scene *s = scenes[g];
+        DeviceGuard guard(s->device);
+        CUDA_TRY(cudaStreamSynchronize(s->own_stream));
+        if (stats && height > (uint32_t)g) {
+            float ms = 0.0f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+            if (ms > kmax) kmax = ms;
+        }
+    }
+    {
+        DeviceGuard guard(root->device);
+        CUDA_TRY(cudaMemcpy(rgba_out, frame, row_bytes * height, cudaMemcpyDefault));
+    }
+    if (stats) {
+        stats->kernel_ms = kmax;
+        stats->total_ms = now_ms() - t0;
+        stats->primary_rays = (uint64_t)width * height * spp * spp;
+        stats->kernel_launches = (uint32_t)ngpu;
+        stats->gpus = (uint32_t)ngpu;
+    }
+    return RT_OK;
+}
+
+int rt_count_rays(const rt_scene *s, const rt_camera *camera, uint32_t width, uint32_t height, uint32_t spp,
+                  uint32_t row_start, uint32_t row_stride, uint32_t row_count, uint64_t *primary, uint64_t *shadow) {
+    if (!primary || !shadow) return fail(RT_ERR_INVALID, "NULL argument");
+    uint64_t hits = 0;
+    *primary = (uint64_t)width * row_count * spp * spp;
+    *shadow = 0;
+    return render_rows_impl(const_cast<rt_scene *>(s), camera, width, height, spp, row_start, row_stride, row_count,
+                            nullptr, 0, nullptr, nullptr, nullptr, &hits, shadow);
+}
+
+int rt_trace_rays(const rt_scene *s, size_t n, const rt_ray *rays, rt_hit *hits) {
+    if (!s || (n && (!rays || !hits))) return fail(RT_ERR_INVALID, "NULL argument");
+    if (n == 0) return RT_OK;
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(RT_ERR_CUDA, "cannot select device %d", s->device);
+    float *d_rays = nullptr, *d_hits = nullptr;
+    CUDA_TRY(cudaMalloc(&d_rays, n * sizeof(rt_ray)));
+    cudaError_t e = cudaMalloc(&d_hits, n * sizeof(rt_hit));
+    if (e == cudaSuccess) e = cudaMemcpy(d_rays, rays, n * sizeof(rt_ray), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = rt_launch_trace_rays(s->d_sph, s->d_skip, s->n, n, d_rays, d_hits, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(hits, d_hits, n * sizeof(rt_hit), cudaMemcpyDeviceToHost);
+    cudaFree(d_rays);
+    if (d_hits) cudaFree(d_hits);
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, "trace_rays: %s", cudaGetErrorString(e));
+    return RT_OK;
+}
+
+int rt_microbench_fp32(int device, int mode, double *tflops) {
+    if (!tflops) return fail(RT_ERR_INVALID, "NULL argument");
+    if (device < 0 || device >= rt_device_count()) return fail(RT_ERR_CUDA, "no CUDA device %d", device);
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    float *d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_out, 64));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int blocks = prop.multiProcessorCount * 8;
+    const int iters = 20000;
+    cudaError_t e = rt_launch_fp32_peak(mode, d_out, blocks, 2000, nullptr);  // warm-up / clock ramp
+    if (e == cudaSuccess) e = cudaEventRecord(e0);
+    if (e == cudaSuccess) e = rt_launch_fp32_peak(mode, d_out, blocks, iters, nullptr);
+    if (e == cudaSuccess) e = cudaEventRecord(e1);
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    float ms = 0.0f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, "fp32 microbench: %s", cudaGetErrorString(e));
+    // 16 chains per thread; FFMA = 2 flop, FMUL+FADD pair = 2 flop in two instructions
+    const double flop = (double)blocks * 256.0 * (double)iters * 16.0 * 2.0;
+    *tflops = flop / (ms * 1e-3) / 1e12;
+    return RT_OK;
+}
+
+int rt_measure_fp32_peak(int device, double *tflops, double *sm_clock_mhz) {
+    int rc = rt_microbench_fp32(device, 0, tflops);
+    if (rc != RT_OK) return rc;
+    if (sm_clock_mhz) {
+        cudaDeviceProp prop;
+        DeviceGuard guard(device);
+        CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+        // effective clock implied by the measured rate: 128 FFMA lanes per SM per cycle
+        *sm_clock_mhz = *tflops * 1e12 / (2.0 * 128.0 * prop.multiProcessorCount) / 1e6;
+    }
+    return RT_OK;
+}
+
+int rt_host_alloc(size_t bytes, void **out) {
+    if (!out) return fail(RT_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (rt_device_count() == 0) return fail(RT_ERR_CUDA, "no CUDA device");
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) return fail(RT_ERR_NOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return RT_OK;
+}
+
+void rt_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

@@ -1,0 +1,293 @@
+// rt_kernels.cu -- sm_100a kernels for the rust-tracer hot path.
+//
+// One fused kernel per variant does, per pixel: ray generation (render.rs:238-243),
+// primary closest-hit traversal (group.rs:72-83, primitive.rs:55-84), shading and
+// the shadow ray (render.rs:188-214), spp^2 accumulation in the reference's sample
+// order (render.rs:236-250) and RGBA8 quantisation (render.rs:92-109); the
+// framebuffer is written exactly once.
+//
+// Variants (all bit-identical to the oracle by construction):
+//   LANE  one thread per pixel; every lane walks the pre-order skip-pointer array
+//         on its own (the direct stackless restatement of the recursion).
+//   WARP  a warp owns an 8x4 pixel tile and walks the array ONCE for all 32 rays:
+//         the node index is warp-uniform (one broadcast load per node), every lane
+//         keeps the reference's own prune decision in a `resume` index (the lane
+//         sleeps until the walk leaves the subtree it pruned), and a ballot
+//         decides whether the walk descends or takes the skip link.
+#include "rt_device.cuh"
+#include "rt_kernels.h"
+
+namespace rt {
+
+static constexpr unsigned FULL = 0xffffffffu;
+static constexpr int TILE_W = 8, TILE_H = 4;      // pixels per warp
+static constexpr int WARPS_X = 4, WARPS_Y = 2;    // warps per block
+static constexpr int BLOCK_THREADS = 32 * WARPS_X * WARPS_Y;
+
+// ---------------------------------------------------------------------------
+// LANE traversal: per-lane stackless walk, exactly the reference recursion.
+// ---------------------------------------------------------------------------
+template <bool ANY>
+RT_DEV void lane_traverse(const float4 *__restrict__ sph, const uint32_t *__restrict__ skip, uint32_t n, V3 o, V3 d,
+                          float &hitd, uint32_t &hit_idx) {
+    uint32_t i = 0;
+    while (i < n) {
+        float4 s = __ldg(&sph[i]);
+        uint32_t sk = __ldg(&skip[i]);
+        if (sk > i + 1) {  // group bound: group.rs:73-75
+            bool enter;
+            if (ANY)
+                enter = sphere_hit_any(s, o, d);
+            else
+                enter = !(sphere_distance(s, o, d) >= hitd);
+            i = enter ? i + 1 : sk;
+        } else {  // leaf: primitive.rs:77-84
+            if (ANY) {
+                if (sphere_hit_any(s, o, d)) {
+                    hitd = 0.0f;
+                    return;
+                }
+            } else {
+                float dist = sphere_distance(s, o, d);
+                if (!(dist >= hitd)) {
+                    hitd = dist;
+                    hit_idx = i;
+                }
+            }
+            i = i + 1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// WARP traversal: warp-uniform walk, per-lane reference prune state.
+// ---------------------------------------------------------------------------
+template <bool ANY>
+RT_DEV void warp_traverse(const float4 *__restrict__ sph, const uint32_t *__restrict__ skip, uint32_t n, bool lane_on,
+                          V3 o, V3 d, float &hitd, uint32_t &hit_idx) {
+    if (!__any_sync(FULL, lane_on)) return;
+    uint32_t resume = lane_on ? 0u : n;  // first node index at which this lane is awake again
+    uint32_t i = 0;
+    while (i < n) {
+        float4 s = __ldg(&sph[i]);
+        uint32_t sk = __ldg(&skip[i]);
+        bool act = i >= resume;
+        if (sk > i + 1) {  // group bound (warp-uniform branch)
+            bool enter = false;
+            if (act) {
+                if (ANY)
+                    enter = sphere_hit_any(s, o, d);
+                else
+                    enter = !(sphere_distance(s, o, d) >= hitd);
+                if (!enter) resume = sk;  // this lane pruned the subtree (group.rs:73-75)
+            }
+            i = __any_sync(FULL, enter) ? i + 1 : sk;
+        } else {  // leaf
+            if (act) {
+                if (ANY) {
+                    if (sphere_hit_any(s, o, d)) {
+                        hitd = 0.0f;
+                        resume = n;  // any-hit: has_missed() is already false
+                    }
+                } else {
+                    float dist = sphere_distance(s, o, d);
+                    if (!(dist >= hitd)) {
+                        hitd = dist;
+                        hit_idx = i;
+                    }
+                }
+            }
+            i = i + 1;
+            if (ANY) {
+                if (!__any_sync(FULL, resume < n)) return;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// The fused pixel kernel.
+// ---------------------------------------------------------------------------
+template <int VARIANT, bool DIAG>
+__global__ void __launch_bounds__(BLOCK_THREADS) render_kernel(const RenderParams p) {
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t x = blockIdx.x * (TILE_W * WARPS_X) + (warp % WARPS_X) * TILE_W + (lane % TILE_W);
+    const uint32_t j = blockIdx.y * (TILE_H * WARPS_Y) + (warp / WARPS_X) * TILE_H + (lane / TILE_W);
+    const bool inside = x < p.width && j < p.row_count;
+    if (VARIANT == RT_KERNEL_LANE && !inside) return;
+    const uint32_t y = p.row_start + j * p.row_stride;
+
+    const ShadeConsts K = shade_consts();
+    const V3 eye = v3(p.eye[0], p.eye[1], p.eye[2]);
+    const V3 light = v3(p.light[0], p.light[1], p.light[2]);
+    const V3 to_light = vmulf(light, -1.0f);                  // render.rs:206
+    const float sqrt_eps = fsqrt(1.1920928955078125e-07f);   // f32::EPSILON.sqrt(), render.rs:199
+
+    V3 c = v3(0.0f, 0.0f, 0.0f);
+    float alpha = 0.0f;
+    unsigned n_hits = 0, n_shadow = 0;
+
+    for (uint32_t ssx = 0; ssx < p.spp; ssx++) {
+        for (uint32_t ssy = 0; ssy < p.spp; ssy++) {
+            V3 d = primary_dir(p, x, y, ssx, ssy);
+            float hitd = RT_INF;
+            uint32_t hit_idx = 0;
+            if (VARIANT == RT_KERNEL_LANE)
+                lane_traverse<false>(p.sph, p.skip, p.n_nodes, eye, d, hitd, hit_idx);
+            else
+                warp_traverse<false>(p.sph, p.skip, p.n_nodes, inside, eye, d, hitd, hit_idx);
+
+            uint8_t kind;
+            bool want_shadow = false;
+            float g = 0.0f;
+            V3 sp = v3(0.0f, 0.0f, 0.0f);
+            if (hitd == RT_INF) {  // render.rs:190-193
+                c = vadd(c, K.background);
+                kind = K_BACKGROUND;
+            } else {
+                n_hits++;
+                V3 nrm = hit_normal(__ldg(&p.sph[hit_idx]), eye, d, hitd);
+                g = vdot(nrm, light);  // render.rs:194
+                if (g >= 0.0f) {       // render.rs:195-198
+                    c = vadd(c, K.ambient);
+                    kind = K_AWAY;
+                } else {
+                    // render.rs:199: (pos + dir*distance) + normal*(distance*sqrt(EPSILON))
+                    sp = vadd(vadd(eye, vmulf(d, hitd)), vmulf(nrm, fmul(hitd, sqrt_eps)));
+                    want_shadow = true;
+                    kind = K_LIT;
+                }
+            }
+            float sh = RT_INF;
+            uint32_t dummy = 0;
+            if (VARIANT == RT_KERNEL_LANE) {
+                if (want_shadow) lane_traverse<true>(p.sph, p.skip, p.n_nodes, sp, to_light, sh, dummy);
+            } else {
+                warp_traverse<true>(p.sph, p.skip, p.n_nodes, want_shadow && inside, sp, to_light, sh, dummy);
+            }
+            if (want_shadow) {
+                n_shadow++;
+                float ng = -g;
+                if (sh == RT_INF) {  // render.rs:208-210
+                    c = vadd(vadd(c, vmulf(K.object, ng)), K.ambient);
+                    alpha = fadd(alpha, 1.0f);
+                } else {  // render.rs:211-214
+                    c = vadd(vadd(c, K.background), vmulf(K.ambient, ng));
+                    kind = K_SHADOWED;
+                }
+            }
+            if (DIAG && p.kinds && inside)
+                p.kinds[((size_t)j * p.width + x) * (p.spp * p.spp) + ssx * p.spp + ssy] = kind;
+        }
+    }
+
+    if (inside) {
+        float recip = frecip(fmul((float)p.spp, (float)p.spp));  // render.rs:219-220
+        c = vmulf(c, recip);
+        alpha = fmul(alpha, recip);
+        uint32_t px = scale_u8(c.x) | (scale_u8(c.y) << 8) | (scale_u8(c.z) << 16) | (scale_u8(alpha) << 24);
+        *reinterpret_cast<uint32_t *>(p.out + (size_t)j * p.pitch + (size_t)x * 4) = px;
+    }
+    if (DIAG && p.ray_counters) {
+        if (!inside) {
+            n_hits = 0;
+            n_shadow = 0;
+        }
+        if (VARIANT == RT_KERNEL_LANE) {
+            atomicAdd(&p.ray_counters[0], (unsigned long long)n_hits);
+            atomicAdd(&p.ray_counters[1], (unsigned long long)n_shadow);
+        } else {
+            n_hits = __reduce_add_sync(FULL, n_hits);
+            n_shadow = __reduce_add_sync(FULL, n_shadow);
+            if (lane == 0) {
+                atomicAdd(&p.ray_counters[0], (unsigned long long)n_hits);
+                atomicAdd(&p.ray_counters[1], (unsigned long long)n_shadow);
+            }
+        }
+    }
+}
+
+// Closest-hit traversal of arbitrary rays (rt_trace_rays): group.rs:72-83 from Hit::missed().
+__global__ void trace_rays_kernel(const float4 *__restrict__ sph, const uint32_t *__restrict__ skip, uint32_t n,
+                                  size_t n_rays, const float *__restrict__ rays, float *__restrict__ hits) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rays) return;
+    V3 o = v3(rays[i * 6 + 0], rays[i * 6 + 1], rays[i * 6 + 2]);
+    V3 d = v3(rays[i * 6 + 3], rays[i * 6 + 4], rays[i * 6 + 5]);
+    float hitd = RT_INF;
+    uint32_t idx = 0;
+    lane_traverse<false>(sph, skip, n, o, d, hitd, idx);
+    V3 nrm = v3(0.0f, 0.0f, 0.0f);
+    if (hitd != RT_INF) nrm = hit_normal(__ldg(&sph[idx]), o, d, hitd);
+    hits[i * 4 + 0] = hitd;
+    hits[i * 4 + 1] = nrm.x;
+    hits[i * 4 + 2] = nrm.y;
+    hits[i * 4 + 3] = nrm.z;
+}
+
+// Register-resident FP32 chains: the live roofline denominator.
+// mode 0: FFMA; mode 1: alternating FMUL / FADD (the unfused mix the parity rule forces).
+template <int MODE>
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float *out, int iters, float a, float b) {
+    float r[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) r[k] = (float)(threadIdx.x + k) * 1e-3f;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            if (MODE == 0) {
+                r[k] = __fmaf_rn(r[k], a, b);
+            } else {
+                r[k] = __fmul_rn(r[k], a);
+                r[k] = __fadd_rn(r[k], b);
+            }
+        }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 16; k++) s += r[k];
+    if (s == 12345.678f) out[0] = s;  // keep the chains alive
+}
+
+}  // namespace rt
+
+// ---------------------------------------------------------------------------
+// Host-side launchers (called from rt_api.cpp through rt_kernels.h).
+// ---------------------------------------------------------------------------
+using namespace rt;
+
+cudaError_t rt_launch_render(int variant, bool diag, const RenderParams &p, cudaStream_t stream) {
+    dim3 block(BLOCK_THREADS);
+    dim3 grid((p.width + TILE_W * WARPS_X - 1) / (TILE_W * WARPS_X),
+              (p.row_count + TILE_H * WARPS_Y - 1) / (TILE_H * WARPS_Y));
+    if (grid.x == 0 || grid.y == 0) return cudaSuccess;
+    if (variant == RT_KERNEL_LANE) {
+        if (diag)
+            render_kernel<RT_KERNEL_LANE, true><<<grid, block, 0, stream>>>(p);
+        else
+            render_kernel<RT_KERNEL_LANE, false><<<grid, block, 0, stream>>>(p);
+    } else {
+        if (diag)
+            render_kernel<RT_KERNEL_WARP, true><<<grid, block, 0, stream>>>(p);
+        else
+            render_kernel<RT_KERNEL_WARP, false><<<grid, block, 0, stream>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t rt_launch_trace_rays(const float4 *sph, const uint32_t *skip, uint32_t n, size_t n_rays,
+                                 const float *rays, float *hits, cudaStream_t stream) {
+    if (n_rays == 0) return cudaSuccess;
+    unsigned blocks = (unsigned)((n_rays + 127) / 128);
+    trace_rays_kernel<<<blocks, 128, 0, stream>>>(sph, skip, n, n_rays, rays, hits);
+    return cudaGetLastError();
+}
+
+cudaError_t rt_launch_fp32_peak(int mode, float *out, int blocks, int iters, cudaStream_t stream) {
+    if (mode == 0)
+        fp32_peak_kernel<0><<<blocks, 256, 0, stream>>>(out, iters, 1.0000001f, 1e-7f);
+    else
+        fp32_peak_kernel<1><<<blocks, 256, 0, stream>>>(out, iters, 1.0000001f, 1e-7f);
+    return cudaGetLastError();
+}

@@ -1,0 +1,16 @@
+// rt_kernels.h -- host-side launch interface of rt_kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+enum { RT_KERNEL_LANE = 1, RT_KERNEL_WARP = 2 };
+
+namespace rt {
+struct RenderParams;
+}
+
+cudaError_t rt_launch_render(int variant, bool diag, const rt::RenderParams &p, cudaStream_t stream);
+cudaError_t rt_launch_trace_rays(const float4 *sph, const uint32_t *skip, uint32_t n, size_t n_rays,
+                                 const float *rays, float *hits, cudaStream_t stream);
+cudaError_t rt_launch_fp32_peak(int mode, float *out, int blocks, int iters, cudaStream_t stream);

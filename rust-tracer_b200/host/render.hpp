@@ -1,0 +1,214 @@
+// render.hpp -- host-side mirror of the reference crate's public interface
+// (src/rust/lib.rs:8: Scene, Renderer, RenderOptions, PPMStdoutRGBABufferWriter,
+// FileOrAnyWriter) over the C ABI of librtrace_b200.so.
+//
+// The names, argument meaning and error behaviour follow src/rust/render.rs; what
+// changed is the engine underneath Renderer::render: the thread pool + bounded
+// channel of 64x64 buckets (render.rs:271-307) became one fused CUDA launch per
+// GPU and a strided gather of row bands.  The writer trait is kept as the seam
+// for output sinks (render.rs:20-30).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <unistd.h>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "rtrace.h"
+
+namespace sphere_tracer {
+
+// A failed `assert!`/`unwrap()` in the reference is a panic (exit code 101).
+struct Panic : std::runtime_error {
+    explicit Panic(const std::string &m) : std::runtime_error(m) {}
+};
+
+inline void rt_check(int rc, const char *what) {
+    if (rc != RT_OK) throw Panic(std::string(what) + ": " + rt_last_error());
+}
+
+// render.rs:33-38
+struct RenderOptions {
+    uint16_t width = 1024;
+    uint16_t height = 1024;
+    uint16_t samples_per_pixel = 1;
+};
+
+// render.rs:42-72 (t > b; b is the upper image row)
+struct ImageRegion {
+    uint16_t l = 0, t = 0, r = 0, b = 0;
+    uint16_t width() const { return r - l; }
+    uint16_t height() const { return t - b; }
+    size_t area() const { return (size_t)width() * height(); }
+    bool contains(const ImageRegion &o) const { return o.l >= l && o.b >= b && o.t <= t && o.r <= r; }
+    size_t buffer_offset(uint16_t x, uint16_t y) const { return (size_t)(y - b) * width() + (size_t)(x - l); }
+    bool operator==(const ImageRegion &o) const { return l == o.l && t == o.t && r == o.r && b == o.b; }
+};
+
+// render.rs:74-135.  Pixels live in pinned host memory so the device-to-host copy
+// of a frame runs at PCIe rate.
+class RGBABuffer {
+  public:
+    explicit RGBABuffer(const ImageRegion &r) : reg_(r), len_(r.area() * components()) {
+        void *p = nullptr;
+        rt_check(rt_host_alloc(len_, &p), "RGBABuffer::new");
+        buf_ = static_cast<uint8_t *>(p);
+    }
+    ~RGBABuffer() { rt_host_free(buf_); }
+    RGBABuffer(const RGBABuffer &) = delete;
+    RGBABuffer &operator=(const RGBABuffer &) = delete;
+    static size_t components() { return 4; }
+    uint8_t *data() { return buf_; }
+    const uint8_t *buffer() const { return buf_; }
+    size_t len() const { return len_; }
+    const ImageRegion &region() const { return reg_; }
+
+    // render.rs:112-126
+    void set_pixels_from_buffer(const RGBABuffer &b) {
+        if (!reg_.contains(b.reg_)) throw Panic("assertion failed: self.reg.contains(&b.reg)");
+        if (reg_ == b.reg_) {
+            memcpy(buf_, b.buf_, len_);
+            return;
+        }
+        size_t w = (size_t)b.reg_.width() * components();
+        for (uint16_t y = b.reg_.b; y < b.reg_.t; y++) {
+            size_t bl = reg_.buffer_offset(b.reg_.l, y) * components();
+            size_t their_bl = b.reg_.buffer_offset(b.reg_.l, y) * components();
+            memcpy(buf_ + bl, b.buf_ + their_bl, w);
+        }
+    }
+
+  private:
+    ImageRegion reg_;
+    size_t len_;
+    uint8_t *buf_ = nullptr;
+};
+
+// render.rs:20-30
+struct RGBABufferWriter {
+    virtual ~RGBABufferWriter() {}
+    virtual void begin(uint16_t x, uint16_t y) = 0;
+    virtual void write_rgba_buffer(const RGBABuffer &buffer) = 0;
+};
+
+// render.rs:313-316
+struct FileOrAnyWriter {
+    FILE *f = nullptr;
+    bool is_file = false;
+    static FileOrAnyWriter any_writer_stdout() { return FileOrAnyWriter{stdout, false}; }
+    static FileOrAnyWriter file_writer(FILE *fp) { return FileOrAnyWriter{fp, true}; }
+};
+
+// render.rs:319-434: P6 (rgb) or P5 (grey) with the alpha channel stripped; the
+// whole image is (re)written from the top each time; final write on destruction.
+// The once-per-second progressive rewrite (render.rs:427-432) degenerates to a
+// single write here because the frame arrives in one buffer.
+class PPMStdoutRGBABufferWriter : public RGBABufferWriter {
+  public:
+    PPMStdoutRGBABufferWriter(bool write_rgb, FileOrAnyWriter *writer) : out_(writer), rgb_(write_rgb) {}
+    ~PPMStdoutRGBABufferWriter() override {
+        try {
+            write_buffer_with_header();
+        } catch (...) {
+        }
+    }
+    void begin(uint16_t x, uint16_t y) override {
+        width_ = x;
+        height_ = y;
+        have_dims_ = true;
+        ImageRegion r;
+        r.l = 0, r.r = x, r.b = 0, r.t = y;
+        image_.reset(new RGBABuffer(r));
+    }
+    void write_rgba_buffer(const RGBABuffer &buffer) override {
+        if (!image_) throw Panic("called `Option::unwrap()` on a `None` value");
+        image_->set_pixels_from_buffer(buffer);
+        dirty_ = true;
+        if (out_->is_file) write_buffer_with_header();  // first flush is immediate (render.rs:427-431)
+    }
+
+  private:
+    void write_buffer_with_header() {
+        if (!dirty_) return;
+        FILE *f = out_->f;
+        if (out_->is_file) {
+            fflush(f);
+            if (ftruncate(fileno(f), 0) != 0) throw Panic("set_len(0) failed");
+            rewind(f);
+        }
+        if (!have_dims_) throw Panic("begin() called");
+        fprintf(f, "%s\n%u %u\n255\n", rgb_ ? "P6" : "P5", (unsigned)width_, (unsigned)height_);
+        const uint8_t *buf = image_->buffer();
+        const size_t n = image_->len() / 4;
+        std::vector<uint8_t> line;
+        line.resize(n * (rgb_ ? 3 : 1));
+        for (size_t i = 0; i < n; i++) {
+            const uint8_t *b = buf + i * 4;
+            if (rgb_) {
+                line[i * 3 + 0] = b[0];
+                line[i * 3 + 1] = b[1];
+                line[i * 3 + 2] = b[2];
+            } else {
+                line[i] = (uint8_t)(((float)b[0] + (float)b[1] + (float)b[2]) / 3.0f);  // render.rs:399
+            }
+        }
+        if (fwrite(line.data(), 1, line.size(), f) != line.size()) throw Panic("write_all failed");
+        fflush(f);
+        dirty_ = false;
+    }
+    FileOrAnyWriter *out_;
+    uint16_t width_ = 0, height_ = 0;
+    bool have_dims_ = false;
+    std::unique_ptr<RGBABuffer> image_;
+    bool rgb_;
+    bool dirty_ = false;
+};
+
+// render.rs:138-167: one replica of the flattened scene per GPU.
+class Scene {
+  public:
+    // Scene::default() generalised by `level`; replicated on devices 0..gpus-1.
+    explicit Scene(uint32_t level = 8, int gpus = 1) {
+        const float origin[3] = {0.0f, -1.0f, 0.0f}, light[3] = {-1.0f, -3.0f, 2.0f}, eye[3] = {0.0f, 0.0f, -4.0f};
+        for (int g = 0; g < gpus; g++) {
+            if (gpus > 1 || g > 0) rt_check(set_device(g), "cudaSetDevice");
+            rt_scene *s = nullptr;
+            rt_check(rt_scene_create(level, origin, 1.0f, light, eye, &s), "Scene::default");
+            replicas_.push_back(s);
+        }
+        if (gpus > 1) set_device(0);
+    }
+    ~Scene() {
+        for (rt_scene *s : replicas_) rt_scene_destroy(s);
+    }
+    Scene(const Scene &) = delete;
+    Scene &operator=(const Scene &) = delete;
+    int gpus() const { return (int)replicas_.size(); }
+    rt_scene *const *replicas() const { return replicas_.data(); }
+
+  private:
+    static int set_device(int g) { return rt_set_device(g); }
+    std::vector<rt_scene *> replicas_;
+};
+
+struct Renderer {
+    // render.rs:260-310.  `camera` (extension) may be NULL.  Sizes need not be
+    // multiples of 64 (the reference asserts they are, render.rs:265-266).
+    static void render(const RenderOptions &o, const Scene &scene, RGBABufferWriter &writer,
+                       const rt_camera *camera = nullptr, rt_stats *stats = nullptr) {
+        writer.begin(o.width, o.height);
+        ImageRegion full;
+        full.l = 0, full.r = o.width, full.b = 0, full.t = o.height;
+        RGBABuffer frame(full);
+        rt_check(rt_render_frame_multi(scene.replicas(), scene.gpus(), camera, o.width, o.height, o.samples_per_pixel,
+                                       frame.data(), frame.len(), stats),
+                 "Renderer::render");
+        writer.write_rgba_buffer(frame);
+    }
+};
+
+}  // namespace sphere_tracer

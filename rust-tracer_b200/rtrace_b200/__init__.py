@@ -1,0 +1,337 @@
+"""rtrace_b200 -- ctypes binding of librtrace_b200.so (include/rtrace.h).
+
+A thin mirror of the reference crate's public surface (src/rust/lib.rs:8:
+``Scene, Renderer, RenderOptions``) over the C ABI, used by the parity tests and
+bench.py.  Nothing here computes pixels: every call goes through the CUDA library
+and raises ``RtError`` when it fails (there is no CPU fallback).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PKG_DIR = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(PKG_DIR, "librtrace_b200.so")
+
+RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_NOMEM, RT_ERR_BUFFER = 0, -1, -2, -3, -4
+VARIANT_AUTO, VARIANT_LANE, VARIANT_WARP, VARIANT_TILE = 0, 1, 2, 3
+
+# every symbol include/rtrace.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = [
+    "rt_last_error", "rt_version", "rt_device_count", "rt_set_device", "rt_set_variant",
+    "rt_scene_create", "rt_scene_create_default", "rt_scene_create_from_nodes", "rt_scene_destroy",
+    "rt_scene_counts", "rt_scene_export_nodes", "rt_flatten_pyramid_host", "rt_scene_light", "rt_scene_eye",
+    "rt_scene_device", "rt_render_region", "rt_render_rows", "rt_render_frame", "rt_render_frame_multi",
+    "rt_count_rays", "rt_trace_rays", "rt_measure_fp32_peak", "rt_microbench_fp32", "rt_host_alloc", "rt_host_free",
+]
+
+
+class RtError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("rtrace_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Camera(C.Structure):
+    _fields_ = [("eye", C.c_float * 3), ("right", C.c_float * 3), ("up", C.c_float * 3), ("forward", C.c_float * 3)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("primary_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("kernel_ms", C.c_double),
+                ("total_ms", C.c_double), ("kernel_launches", C.c_uint32), ("gpus", C.c_uint32)]
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; fail loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s is missing: run `make lib` (or __graft_entry__.build()); there is no fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, u32, u16, f32p, u8p = C.c_void_p, C.c_uint32, C.c_uint16, C.POINTER(C.c_float), C.c_void_p
+    u64p, u32p = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
+    L.rt_last_error.restype = C.c_char_p
+    L.rt_version.restype = C.c_char_p
+    L.rt_device_count.restype = C.c_int
+    L.rt_set_variant.argtypes = [C.c_int]
+    L.rt_set_device.argtypes = [C.c_int]
+    L.rt_scene_create.argtypes = [u32, f32p, C.c_float, f32p, f32p, C.POINTER(vp)]
+    L.rt_scene_create_default.argtypes = [C.POINTER(vp)]
+    L.rt_scene_create_from_nodes.argtypes = [u32, f32p, u32p, f32p, f32p, C.POINTER(vp)]
+    L.rt_scene_destroy.argtypes = [vp]
+    L.rt_scene_destroy.restype = None
+    L.rt_scene_counts.argtypes = [vp, u64p, u64p]
+    L.rt_scene_export_nodes.argtypes = [vp, f32p, u32p, u32, u32p]
+    L.rt_flatten_pyramid_host.argtypes = [u32, f32p, C.c_float, f32p, u32p, u32, u32p]
+    L.rt_scene_light.argtypes = [vp, f32p]
+    L.rt_scene_eye.argtypes = [vp, f32p]
+    L.rt_scene_device.argtypes = [vp]
+    L.rt_render_region.argtypes = [vp, u16, u16, u16, u16, u16, u16, u16, u8p, C.c_size_t]
+    L.rt_render_rows.argtypes = [vp, C.POINTER(Camera), u32, u32, u32, u32, u32, u32, u8p, C.c_size_t, u8p, vp,
+                                 C.POINTER(Stats)]
+    L.rt_render_frame.argtypes = [vp, C.POINTER(Camera), u32, u32, u32, u8p, C.c_size_t, C.POINTER(Stats)]
+    L.rt_render_frame_multi.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(Camera), u32, u32, u32, u8p, C.c_size_t,
+                                        C.POINTER(Stats)]
+    L.rt_count_rays.argtypes = [vp, C.POINTER(Camera), u32, u32, u32, u32, u32, u32, u64p, u64p]
+    L.rt_trace_rays.argtypes = [vp, C.c_size_t, vp, vp]
+    L.rt_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.rt_microbench_fp32.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
+    L.rt_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.rt_host_free.argtypes = [vp]
+    L.rt_host_free.restype = None
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != RT_OK:
+        raise RtError(rc, lib().rt_last_error().decode("utf-8", "replace"))
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def device_count():
+    return int(lib().rt_device_count())
+
+
+def version():
+    return lib().rt_version().decode()
+
+
+def set_device(d):
+    _check(lib().rt_set_device(int(d)))
+
+
+def set_variant(v):
+    _check(lib().rt_set_variant(int(v)))
+
+
+def make_camera(eye, right=(1, 0, 0), up=(0, 1, 0), forward=(0, 0, 1)):
+    cam = Camera()
+    cam.eye[:] = [float(x) for x in eye]
+    cam.right[:] = [float(x) for x in right]
+    cam.up[:] = [float(x) for x in up]
+    cam.forward[:] = [float(x) for x in forward]
+    return cam
+
+
+def orbit_camera(frame, n_frames, eye=(0.0, 0.0, -4.0)):
+    """Camera extension: the reference camera rotated about the flake's
+    vertical axis by 2 pi frame / n_frames.  Frame 0 is the reference camera."""
+    import math
+    th = 2.0 * math.pi * frame / n_frames
+    c, s = math.cos(th), math.sin(th)
+    if frame % n_frames == 0:
+        c, s = 1.0, 0.0
+
+    def rot(v):
+        return (c * v[0] + s * v[2], v[1], -s * v[0] + c * v[2])
+
+    return make_camera(rot(eye), rot((1, 0, 0)), (0, 1, 0), rot((0, 0, 1)))
+
+
+def flatten_pyramid_host(level, origin=(0.0, -1.0, 0.0), radius=1.0):
+    """Host-only scene flattening (no GPU needed)."""
+    n = C.c_uint32()
+    _check(lib().rt_flatten_pyramid_host(level, _f3(origin), radius, None, None, 0, C.byref(n)))
+    sph = np.empty((n.value, 4), np.float32)
+    sk = np.empty(n.value, np.uint32)
+    _check(lib().rt_flatten_pyramid_host(level, _f3(origin), radius, _fp(sph), sk.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                         n.value, C.byref(n)))
+    return sph, sk
+
+
+class RenderOptions:
+    """render.rs:33-38"""
+
+    def __init__(self, width=1024, height=1024, samples_per_pixel=1):
+        self.width, self.height, self.samples_per_pixel = int(width), int(height), int(samples_per_pixel)
+
+
+class Scene:
+    """render.rs:138-167 ``Scene``; ``Scene()`` is ``Scene::default()``."""
+
+    def __init__(self, level=8, origin=(0.0, -1.0, 0.0), radius=1.0, light=(-1.0, -3.0, 2.0), eye=(0.0, 0.0, -4.0),
+                 _handle=None):
+        self._h = C.c_void_p()
+        if _handle is not None:
+            self._h = _handle
+        else:
+            _check(lib().rt_scene_create(level, _f3(origin), radius, _f3(light), _f3(eye), C.byref(self._h)))
+
+    @classmethod
+    def from_nodes(cls, spheres4, skip, light, eye):
+        sph = np.ascontiguousarray(spheres4, dtype=np.float32)
+        sk = np.ascontiguousarray(skip, dtype=np.uint32)
+        h = C.c_void_p()
+        _check(lib().rt_scene_create_from_nodes(len(sk), _fp(sph), sk.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                _f3(light), _f3(eye), C.byref(h)))
+        return cls(_handle=h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().rt_scene_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def counts(self):
+        g, i = C.c_uint64(), C.c_uint64()
+        _check(lib().rt_scene_counts(self._h, C.byref(g), C.byref(i)))
+        return g.value, i.value
+
+    def export_nodes(self):
+        n = C.c_uint32()
+        _check(lib().rt_scene_export_nodes(self._h, None, None, 0, C.byref(n)))
+        sph = np.empty((n.value, 4), np.float32)
+        sk = np.empty(n.value, np.uint32)
+        _check(lib().rt_scene_export_nodes(self._h, _fp(sph), sk.ctypes.data_as(C.POINTER(C.c_uint32)), n.value,
+                                           C.byref(n)))
+        return sph, sk
+
+    def light(self):
+        v = (C.c_float * 3)()
+        _check(lib().rt_scene_light(self._h, v))
+        return np.array(v[:], np.float32)
+
+    def eye(self):
+        v = (C.c_float * 3)()
+        _check(lib().rt_scene_eye(self._h, v))
+        return np.array(v[:], np.float32)
+
+    def device(self):
+        return int(lib().rt_scene_device(self._h))
+
+    def trace_rays(self, pos, dirs):
+        pos = np.asarray(pos, np.float32).reshape(-1, 3)
+        dirs = np.asarray(dirs, np.float32).reshape(-1, 3)
+        rays = np.ascontiguousarray(np.concatenate([pos, dirs], axis=1), np.float32)
+        hits = np.empty((len(pos), 4), np.float32)
+        _check(lib().rt_trace_rays(self._h, len(pos), rays.ctypes.data, hits.ctypes.data))
+        return hits[:, 0].copy(), hits[:, 1:].copy()
+
+    def count_rays(self, width, height, spp, row_start=0, row_stride=1, row_count=None, camera=None):
+        row_count = height if row_count is None else row_count
+        p, s = C.c_uint64(), C.c_uint64()
+        _check(lib().rt_count_rays(self._h, C.byref(camera) if camera is not None else None, width, height, spp,
+                                   row_start, row_stride, row_count, C.byref(p), C.byref(s)))
+        return p.value, s.value
+
+
+class Renderer:
+    """render.rs:169-311 ``Renderer`` (associated functions only, like the reference)."""
+
+    @staticmethod
+    def render_region(options, scene, l, b, r, t):
+        """Renderer::render_region (render.rs:218-255) -> (t-b, r-l, 4) uint8."""
+        out = np.empty((max(t - b, 0), max(r - l, 0), 4), np.uint8)
+        _check(lib().rt_render_region(scene.handle, options.width, options.height, options.samples_per_pixel,
+                                      l, b, r, t, out.ctypes.data, out.nbytes))
+        return out
+
+    @staticmethod
+    def render_rows(options, scene, row_start=0, row_stride=1, row_count=None, camera=None, kinds=False, out=None,
+                    out_ptr=None, pitch=0, stream=None, want_stats=False):
+        """One GPU's interleaved share of Renderer::render's bucket loop (render.rs:268-309)."""
+        w, h, spp = options.width, options.height, options.samples_per_pixel
+        if row_count is None:
+            row_count = (h - row_start + row_stride - 1) // row_stride
+        kd = None
+        if out_ptr is None:
+            if out is None:
+                out = np.empty((row_count, w, 4), np.uint8)
+            out_ptr = out.ctypes.data
+        if kinds:
+            kd = np.empty((row_count, w, spp * spp), np.uint8)
+        st = Stats() if want_stats else None
+        _check(lib().rt_render_rows(scene.handle, C.byref(camera) if camera is not None else None, w, h, spp,
+                                    row_start, row_stride, row_count, out_ptr, pitch,
+                                    kd.ctypes.data if kd is not None else None, stream,
+                                    C.byref(st) if st is not None else None))
+        res = [out]
+        if kinds:
+            res.append(kd)
+        if want_stats:
+            res.append(st)
+        return res[0] if len(res) == 1 else tuple(res)
+
+    @staticmethod
+    def render(options, scene, camera=None, out=None, out_ptr=None, want_stats=False):
+        """Renderer::render (render.rs:260-310): the whole frame on the scene's GPU."""
+        w, h, spp = options.width, options.height, options.samples_per_pixel
+        if out_ptr is None:
+            if out is None:
+                out = np.empty((h, w, 4), np.uint8)
+            out_ptr = out.ctypes.data
+        st = Stats() if want_stats else None
+        _check(lib().rt_render_frame(scene.handle, C.byref(camera) if camera is not None else None, w, h, spp,
+                                     out_ptr, w * h * 4, C.byref(st) if st is not None else None))
+        return (out, st) if want_stats else out
+
+    @staticmethod
+    def render_multi(options, scenes, camera=None, want_stats=False):
+        """Whole frame on len(scenes) GPUs of this process, rows interleaved, gathered on GPU 0."""
+        w, h, spp = options.width, options.height, options.samples_per_pixel
+        out = np.empty((h, w, 4), np.uint8)
+        arr = (C.c_void_p * len(scenes))(*[s.handle for s in scenes])
+        st = Stats() if want_stats else None
+        _check(lib().rt_render_frame_multi(arr, len(scenes), C.byref(camera) if camera is not None else None, w, h,
+                                           spp, out.ctypes.data, out.nbytes, C.byref(st) if st is not None else None))
+        return (out, st) if want_stats else out
+
+
+def measure_fp32_peak(device=0):
+    t, c = C.c_double(), C.c_double()
+    _check(lib().rt_measure_fp32_peak(device, C.byref(t), C.byref(c)))
+    return t.value, c.value
+
+
+def microbench_fp32(device, mode):
+    t = C.c_double()
+    _check(lib().rt_microbench_fp32(device, mode, C.byref(t)))
+    return t.value
+
+
+class PinnedBuffer:
+    """Pinned host memory from rt_host_alloc, exposed as a numpy array."""
+
+    def __init__(self, nbytes):
+        self._p = C.c_void_p()
+        _check(lib().rt_host_alloc(nbytes, C.byref(self._p)))
+        self.nbytes = nbytes
+        self.array = np.ctypeslib.as_array(C.cast(self._p, C.POINTER(C.c_uint8)), shape=(nbytes,))
+
+    @property
+    def ptr(self):
+        return self._p.value
+
+    def close(self):
+        if self._p:
+            self.array = None
+            lib().rt_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
