@@ -77,13 +77,35 @@ double now_ms() {
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
-int kernel_variant() {
+// A camera basis must be orthonormal for the TILE variant's cone bounds to hold.
+bool orthonormal(const float b[9]) {
+    for (int i = 0; i < 3; i++)
+        for (int j = i; j < 3; j++) {
+            float d = b[3 * i] * b[3 * j] + b[3 * i + 1] * b[3 * j + 1] + b[3 * i + 2] * b[3 * j + 2];
+            if (fabsf(d - (i == j ? 1.0f : 0.0f)) > 1e-5f) return false;
+        }
+    return true;
+}
+
+// AUTO and TILE pick the tile kernel whenever it applies (regular pyramid, spp 1..4,
+// orthonormal camera) and otherwise fall back to the per-lane walk; all variants
+// produce identical bytes.
+int kernel_variant(const rt::RenderParams &p) {
     switch (g_variant) {
         case RT_VARIANT_LANE:
             return RT_KERNEL_LANE;
-        default:
+        case RT_VARIANT_WARP:
             return RT_KERNEL_WARP;
+        default:
+            if (rt_tile_supported(p) && (!p.has_basis || orthonormal(p.basis))) return RT_KERNEL_TILE;
+            return RT_KERNEL_LANE;
     }
+}
+
+cudaError_t launch(const rt::RenderParams &p, bool diag, cudaStream_t stream) {
+    const int v = kernel_variant(p);
+    if (v == RT_KERNEL_TILE) return rt_launch_render_tile(diag, p, stream);
+    return rt_launch_render(v, diag, p, stream);
 }
 
 // true if ptr is device memory; *dev receives its device ordinal
@@ -131,6 +153,7 @@ void fill_params(const rt_scene *s, const rt_camera *cam, uint32_t w, uint32_t h
     p.sph = s->d_sph;
     p.skip = s->d_skip;
     p.n_nodes = s->n;
+    p.level = s->flat.level;
     const float *eye = cam ? cam->eye : s->flat.eye;
     for (int k = 0; k < 3; k++) {
         p.eye[k] = eye[k];
@@ -373,7 +396,7 @@ static int render_rows_impl(rt_scene *s, const rt_camera *camera, uint32_t width
     }
 
     if (stats) CUDA_TRY(cudaEventRecord(s->ev0, stream));
-    CUDA_TRY(rt_launch_render(kernel_variant(), diag, p, stream));
+    CUDA_TRY(launch(p, diag, stream));
     if (stats) CUDA_TRY(cudaEventRecord(s->ev1, stream));
 
     bool must_sync = false;
@@ -500,7 +523,7 @@ int rt_render_frame_multi(rt_scene *const *scenes, int ngpu, const rt_camera *ca
             p.pitch = row_bytes;
         }
         if (stats) CUDA_TRY(cudaEventRecord(s->ev0, s->own_stream));
-        CUDA_TRY(rt_launch_render(kernel_variant(), false, p, s->own_stream));
+        CUDA_TRY(launch(p, false, s->own_stream));
         if (stats) CUDA_TRY(cudaEventRecord(s->ev1, s->own_stream));
         if (g > 0)  // strided peer copy over NVLink: the pitch de-interleaves the band into the frame
             CUDA_TRY(cudaMemcpy2DAsync(frame + row_bytes * g, row_bytes * ngpu, s->d_fb, row_bytes, row_bytes, rows, cudaMemcpyDefault, s->own_stream));

@@ -79,6 +79,7 @@ struct RenderParams {
     const float4 *sph;     // n x {cx,cy,cz,r}, pre-order
     const uint32_t *skip;  // n x next-node-when-pruned; leaf: i+1
     uint32_t n_nodes;
+    uint32_t level;  // pyramid level (regular tree: child offsets follow from the depth); 0 = hand-built tree
     float eye[3];
     float light[3];  // normalised directional light (render.rs:154-159)
     float basis[9];  // right, up, forward (camera extension)

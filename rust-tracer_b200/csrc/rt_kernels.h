@@ -4,7 +4,7 @@
 #include <stddef.h>
 #include <stdint.h>
 
-enum { RT_KERNEL_LANE = 1, RT_KERNEL_WARP = 2 };
+enum { RT_KERNEL_LANE = 1, RT_KERNEL_WARP = 2, RT_KERNEL_TILE = 3 };
 
 namespace rt {
 struct RenderParams;
@@ -14,3 +14,7 @@ cudaError_t rt_launch_render(int variant, bool diag, const rt::RenderParams &p, 
 cudaError_t rt_launch_trace_rays(const float4 *sph, const uint32_t *skip, uint32_t n, size_t n_rays,
                                  const float *rays, float *hits, cudaStream_t stream);
 cudaError_t rt_launch_fp32_peak(int mode, float *out, int blocks, int iters, cudaStream_t stream);
+
+// TILE variant (rt_tile.cu): regular pyramids, 1 <= spp <= 4, orthonormal camera basis.
+bool rt_tile_supported(const rt::RenderParams &p);
+cudaError_t rt_launch_render_tile(bool diag, const rt::RenderParams &p, cudaStream_t stream);
