@@ -39,3 +39,8 @@ image: rtrace
 clean:
 	rm -rf target $(LIB) $(PKG)/build.log
 	$(MAKE) -C oracle clean
+
+# Experiment builds: `make variant NAME=w4 DEFS=-DRT_TILE_WARPS=4` -> build/librtrace_b200_w4.so
+variant:
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) $(DEFS) -shared -x cu $(LIBSRC) -o build/librtrace_b200_$(NAME).so 2> build/$(NAME).log || (cat build/$(NAME).log; false)

@@ -167,6 +167,11 @@ int rt_measure_fp32_peak(int device, double *tflops, double *sm_clock_mhz);
  * flop per FFMA and 1 per FMUL/FADD. */
 int rt_microbench_fp32(int device, int mode, double *tflops);
 
+/* Diagnostics: compares the kernels' branch-free Newton-step sqrt / reciprocal with
+ * the IEEE-rounded intrinsics on n pseudo-random inputs; mismatches[0] = sqrt,
+ * mismatches[1] = reciprocal (both must be 0). */
+int rt_selftest_math(uint32_t n, uint32_t seed, uint64_t mismatches[2]);
+
 /* Pinned host memory for output buffers (what the CLI hands to rt_render_frame so
  * the device-to-host copy runs at full PCIe rate).  Replaces the Vec<u8> of
  * RGBABuffer::new (render.rs:80-85). */

@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -104,7 +105,15 @@ int kernel_variant(const rt::RenderParams &p) {
 
 cudaError_t launch(const rt::RenderParams &p, bool diag, cudaStream_t stream) {
     const int v = kernel_variant(p);
-    if (v == RT_KERNEL_TILE) return rt_launch_render_tile(diag, p, stream);
+    if (v == RT_KERNEL_TILE) {
+        // Small frames are split into 4x more, 4x shorter warp tiles so the launch does not end in a
+        // long tail of a few expensive tiles; big frames amortise each tile's cull over 16 slots per lane.
+        static const char *force = getenv("RTRACE_TILE_SHAPE");
+        const uint64_t samples = (uint64_t)p.width * p.row_count * p.spp * p.spp;
+        int shape = samples < (uint64_t)24 << 20 ? 1 : 0;
+        if (force && *force) shape = atoi(force);
+        return rt_launch_render_tile(diag, p, stream, shape);
+    }
     return rt_launch_render(v, diag, p, stream);
 }
 
@@ -129,7 +138,7 @@ int upload(rt_scene *s) {
     CUDA_TRY(cudaMalloc(&s->d_skip, sizeof(uint32_t) * s->n));
     CUDA_TRY(cudaMemcpy(s->d_sph, s->flat.sph.data(), sizeof(float4) * s->n, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(s->d_skip, s->flat.skip.data(), sizeof(uint32_t) * s->n, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMalloc(&s->d_ctr, sizeof(unsigned long long) * 2));
+    CUDA_TRY(cudaMalloc(&s->d_ctr, sizeof(unsigned long long) * 16));
     CUDA_TRY(cudaEventCreate(&s->ev0));
     CUDA_TRY(cudaEventCreate(&s->ev1));
     CUDA_TRY(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
@@ -154,6 +163,7 @@ void fill_params(const rt_scene *s, const rt_camera *cam, uint32_t w, uint32_t h
     p.skip = s->d_skip;
     p.n_nodes = s->n;
     p.level = s->flat.level;
+    p.leaf_rmin = s->flat.leaf_rmin;
     const float *eye = cam ? cam->eye : s->flat.eye;
     for (int k = 0; k < 3; k++) {
         p.eye[k] = eye[k];
@@ -392,7 +402,7 @@ static int render_rows_impl(rt_scene *s, const rt_camera *camera, uint32_t width
     if (counting) {
         diag = true;
         p.ray_counters = s->d_ctr;
-        CUDA_TRY(cudaMemsetAsync(s->d_ctr, 0, sizeof(unsigned long long) * 2, stream));
+        CUDA_TRY(cudaMemsetAsync(s->d_ctr, 0, sizeof(unsigned long long) * 16, stream));
     }
 
     if (stats) CUDA_TRY(cudaEventRecord(s->ev0, stream));
@@ -408,7 +418,7 @@ static int render_rows_impl(rt_scene *s, const rt_camera *camera, uint32_t width
         CUDA_TRY(cudaMemcpyAsync(kinds_out, s->d_kinds, kinds_bytes, cudaMemcpyDeviceToHost, stream));
         must_sync = true;
     }
-    unsigned long long ctr[2] = {0, 0};
+    unsigned long long ctr[16] = {0};
     if (counting) {
         CUDA_TRY(cudaMemcpyAsync(ctr, s->d_ctr, sizeof(ctr), cudaMemcpyDeviceToHost, stream));
         must_sync = true;
@@ -417,6 +427,11 @@ static int render_rows_impl(rt_scene *s, const rt_camera *camera, uint32_t width
     if (counting) {
         if (count_hits) *count_hits = ctr[0];
         *count_shadow = ctr[1];
+        if (getenv("RTRACE_PROFILE")) {  // phase totals of an -DRT_TILE_PROFILE build
+            fprintf(stderr, "rt-profile:");
+            for (int k = 2; k < 16; k++) fprintf(stderr, " %llu", ctr[k]);
+            fprintf(stderr, "\n");
+        }
     }
     if (stats) {
         float ms = 0.0f;
@@ -607,6 +622,22 @@ int rt_microbench_fp32(int device, int mode, double *tflops) {
     // 16 chains per thread; FFMA = 2 flop, FMUL+FADD pair = 2 flop in two instructions
     const double flop = (double)blocks * 256.0 * (double)iters * 16.0 * 2.0;
     *tflops = flop / (ms * 1e-3) / 1e12;
+    return RT_OK;
+}
+
+int rt_selftest_math(uint32_t n, uint32_t seed, uint64_t mismatches[2]) {
+    if (!mismatches) return fail(RT_ERR_INVALID, "NULL argument");
+    if (rt_device_count() == 0) return fail(RT_ERR_CUDA, "no CUDA device");
+    unsigned long long *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 16));
+    cudaError_t e = cudaMemset(d, 0, 16);
+    if (e == cudaSuccess) e = rt_launch_math_selftest(n, seed, d, nullptr);
+    unsigned long long h[2] = {0, 0};
+    if (e == cudaSuccess) e = cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, "math selftest: %s", cudaGetErrorString(e));
+    mismatches[0] = h[0];
+    mismatches[1] = h[1];
     return RT_OK;
 }
 

@@ -80,6 +80,8 @@ struct RenderParams {
     const uint32_t *skip;  // n x next-node-when-pruned; leaf: i+1
     uint32_t n_nodes;
     uint32_t level;  // pyramid level (regular tree: child offsets follow from the depth); 0 = hand-built tree
+    float leaf_rmin;  // smallest leaf radius (regular pyramid)
+    uint32_t tile_stride;  // TILE variant: warp w renders tile (w * tile_stride) mod n_tiles
     float eye[3];
     float light[3];  // normalised directional light (render.rs:154-159)
     float basis[9];  // right, up, forward (camera extension)

@@ -35,6 +35,8 @@ void flatten_pyramid(uint32_t level, const float origin[3], float radius, FlatSc
     out.skip.reserve(n);
     out.groups = out.items = 0;
     out.level = level;
+    out.leaf_rmin = radius;
+    for (uint32_t l = 1; l < level; l++) out.leaf_rmin *= 0.5f;
 
     // Explicit DFS stack; children are pushed in reverse so they pop in reference order.
     std::vector<Frame> stack;

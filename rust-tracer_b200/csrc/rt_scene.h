@@ -12,6 +12,7 @@ struct FlatScene {
     float light[3] = {0, 0, 0};  // normalised
     float eye[3] = {0, 0, 0};
     uint32_t level = 0;  // 0 for hand-built trees
+    float leaf_rmin = 0.0f;  // smallest leaf radius
 };
 
 // Nodes in a pyramid subtree of the given level: S(1) = 1, S(L) = 2 + 4 S(L-1).

@@ -12,7 +12,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PKG_DIR = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(PKG_DIR, "librtrace_b200.so")
+LIB_PATH = os.environ.get("RTRACE_B200_LIB") or os.path.join(PKG_DIR, "librtrace_b200.so")  # env: kernel experiments
 
 RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_NOMEM, RT_ERR_BUFFER = 0, -1, -2, -3, -4
 VARIANT_AUTO, VARIANT_LANE, VARIANT_WARP, VARIANT_TILE = 0, 1, 2, 3
@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "rt_scene_create", "rt_scene_create_default", "rt_scene_create_from_nodes", "rt_scene_destroy",
     "rt_scene_counts", "rt_scene_export_nodes", "rt_flatten_pyramid_host", "rt_scene_light", "rt_scene_eye",
     "rt_scene_device", "rt_render_region", "rt_render_rows", "rt_render_frame", "rt_render_frame_multi",
-    "rt_count_rays", "rt_trace_rays", "rt_measure_fp32_peak", "rt_microbench_fp32", "rt_host_alloc", "rt_host_free",
+    "rt_count_rays", "rt_trace_rays", "rt_measure_fp32_peak", "rt_microbench_fp32", "rt_selftest_math", "rt_host_alloc", "rt_host_free",
 ]
 
 
@@ -81,6 +81,7 @@ def lib():
     L.rt_trace_rays.argtypes = [vp, C.c_size_t, vp, vp]
     L.rt_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.rt_microbench_fp32.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
+    L.rt_selftest_math.argtypes = [u32, u32, u64p]
     L.rt_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.rt_host_free.argtypes = [vp]
     L.rt_host_free.restype = None
@@ -309,6 +310,12 @@ def microbench_fp32(device, mode):
     t = C.c_double()
     _check(lib().rt_microbench_fp32(device, mode, C.byref(t)))
     return t.value
+
+
+def selftest_math(n=1 << 24, seed=1):
+    m = (C.c_uint64 * 2)()
+    _check(lib().rt_selftest_math(n, seed, m))
+    return int(m[0]), int(m[1])
 
 
 class PinnedBuffer:

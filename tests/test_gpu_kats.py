@@ -62,3 +62,9 @@ def test_random_rays_match_oracle(rt, oracle, gpu_scene8, oracle_scene8):
     assert np.array_equal(gd.view(np.uint32), od.view(np.uint32))
     assert np.array_equal(gn.view(np.uint32), on.view(np.uint32))
     assert 0.2 < np.isfinite(gd).mean() < 1.0
+
+
+def test_newton_sqrt_and_reciprocal_are_ieee_exact(rt):
+    """The TILE kernel's branch-free sqrt / reciprocal must equal __fsqrt_rn / __frcp_rn bit for bit."""
+    for seed in (1, 2, 3, 4):
+        assert rt.selftest_math(1 << 24, seed) == (0, 0)
