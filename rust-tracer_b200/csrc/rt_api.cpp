@@ -106,11 +106,8 @@ int kernel_variant(const rt::RenderParams &p) {
 cudaError_t launch(const rt::RenderParams &p, bool diag, cudaStream_t stream) {
     const int v = kernel_variant(p);
     if (v == RT_KERNEL_TILE) {
-        // Small frames are split into 4x more, 4x shorter warp tiles so the launch does not end in a
-        // long tail of a few expensive tiles; big frames amortise each tile's cull over 16 slots per lane.
-        static const char *force = getenv("RTRACE_TILE_SHAPE");
-        const uint64_t samples = (uint64_t)p.width * p.row_count * p.spp * p.spp;
-        int shape = samples < (uint64_t)24 << 20 ? 1 : 0;
+        static const char *force = getenv("RTRACE_TILE_SHAPE");  // kernel experiments
+        int shape = 0;
         if (force && *force) shape = atoi(force);
         return rt_launch_render_tile(diag, p, stream, shape);
     }

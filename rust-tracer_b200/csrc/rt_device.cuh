@@ -126,4 +126,40 @@ RT_DEV V3 primary_dir(const RenderParams &p, uint32_t x, uint32_t y, uint32_t ss
     return vnormalized(d);
 }
 
+// ---------------------------------------------------------------------------
+// LANE traversal: per-lane stackless walk, exactly the reference recursion.
+// ---------------------------------------------------------------------------
+template <bool ANY>
+RT_DEV void lane_traverse(const float4 *__restrict__ sph, const uint32_t *__restrict__ skip, uint32_t n, V3 o, V3 d,
+                          float &hitd, uint32_t &hit_idx) {
+    uint32_t i = 0;
+    while (i < n) {
+        float4 s = __ldg(&sph[i]);
+        uint32_t sk = __ldg(&skip[i]);
+        if (sk > i + 1) {  // group bound: group.rs:73-75
+            bool enter;
+            if (ANY)
+                enter = sphere_hit_any(s, o, d);
+            else
+                enter = !(sphere_distance(s, o, d) >= hitd);
+            i = enter ? i + 1 : sk;
+        } else {  // leaf: primitive.rs:77-84
+            if (ANY) {
+                if (sphere_hit_any(s, o, d)) {
+                    hitd = 0.0f;
+                    return;
+                }
+            } else {
+                float dist = sphere_distance(s, o, d);
+                if (!(dist >= hitd)) {
+                    hitd = dist;
+                    hit_idx = i;
+                }
+            }
+            i = i + 1;
+        }
+    }
+}
+
+
 }  // namespace rt

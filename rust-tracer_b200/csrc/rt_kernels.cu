@@ -25,41 +25,6 @@ static constexpr int WARPS_X = 4, WARPS_Y = 2;    // warps per block
 static constexpr int BLOCK_THREADS = 32 * WARPS_X * WARPS_Y;
 
 // ---------------------------------------------------------------------------
-// LANE traversal: per-lane stackless walk, exactly the reference recursion.
-// ---------------------------------------------------------------------------
-template <bool ANY>
-RT_DEV void lane_traverse(const float4 *__restrict__ sph, const uint32_t *__restrict__ skip, uint32_t n, V3 o, V3 d,
-                          float &hitd, uint32_t &hit_idx) {
-    uint32_t i = 0;
-    while (i < n) {
-        float4 s = __ldg(&sph[i]);
-        uint32_t sk = __ldg(&skip[i]);
-        if (sk > i + 1) {  // group bound: group.rs:73-75
-            bool enter;
-            if (ANY)
-                enter = sphere_hit_any(s, o, d);
-            else
-                enter = !(sphere_distance(s, o, d) >= hitd);
-            i = enter ? i + 1 : sk;
-        } else {  // leaf: primitive.rs:77-84
-            if (ANY) {
-                if (sphere_hit_any(s, o, d)) {
-                    hitd = 0.0f;
-                    return;
-                }
-            } else {
-                float dist = sphere_distance(s, o, d);
-                if (!(dist >= hitd)) {
-                    hitd = dist;
-                    hit_idx = i;
-                }
-            }
-            i = i + 1;
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------
 // WARP traversal: warp-uniform walk, per-lane reference prune state.
 // ---------------------------------------------------------------------------
 template <bool ANY>
