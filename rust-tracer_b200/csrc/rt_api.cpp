@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -40,6 +41,18 @@ struct rt_scene {
     unsigned long long *d_ctr = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t own_stream = nullptr;
+    // PHASED variant scratch, one set per stream (launches on different streams may overlap)
+    struct Phased {
+        uint32_t *winner = nullptr;
+        size_t winner_cap = 0;
+        uint4 *hdr = nullptr;
+        size_t hdr_cap = 0;
+        uint4 *pool = nullptr;
+        uint32_t pool_units = 0;
+        uint32_t *pool_count = nullptr;
+    };
+    std::map<cudaStream_t, Phased> phased;
+    std::mutex mu_phased;  // guards the map only (mu may already be held by the caller)
 };
 
 namespace {
@@ -76,42 +89,6 @@ struct DeviceGuard {
 double now_ms() {
     using namespace std::chrono;
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
-}
-
-// A camera basis must be orthonormal for the TILE variant's cone bounds to hold.
-bool orthonormal(const float b[9]) {
-    for (int i = 0; i < 3; i++)
-        for (int j = i; j < 3; j++) {
-            float d = b[3 * i] * b[3 * j] + b[3 * i + 1] * b[3 * j + 1] + b[3 * i + 2] * b[3 * j + 2];
-            if (fabsf(d - (i == j ? 1.0f : 0.0f)) > 1e-5f) return false;
-        }
-    return true;
-}
-
-// AUTO and TILE pick the tile kernel whenever it applies (regular pyramid, spp 1..4,
-// orthonormal camera) and otherwise fall back to the per-lane walk; all variants
-// produce identical bytes.
-int kernel_variant(const rt::RenderParams &p) {
-    switch (g_variant) {
-        case RT_VARIANT_LANE:
-            return RT_KERNEL_LANE;
-        case RT_VARIANT_WARP:
-            return RT_KERNEL_WARP;
-        default:
-            if (rt_tile_supported(p) && (!p.has_basis || orthonormal(p.basis))) return RT_KERNEL_TILE;
-            return RT_KERNEL_LANE;
-    }
-}
-
-cudaError_t launch(const rt::RenderParams &p, bool diag, cudaStream_t stream) {
-    const int v = kernel_variant(p);
-    if (v == RT_KERNEL_TILE) {
-        static const char *force = getenv("RTRACE_TILE_SHAPE");  // kernel experiments
-        int shape = 0;
-        if (force && *force) shape = atoi(force);
-        return rt_launch_render_tile(diag, p, stream, shape);
-    }
-    return rt_launch_render(v, diag, p, stream);
 }
 
 // true if ptr is device memory; *dev receives its device ordinal
@@ -194,6 +171,88 @@ int check_frame_args(const rt_scene *s, uint32_t w, uint32_t h, uint32_t spp, ui
     return RT_OK;
 }
 
+// A camera basis must be orthonormal for the TILE variant's cone bounds to hold.
+bool orthonormal(const float b[9]) {
+    for (int i = 0; i < 3; i++)
+        for (int j = i; j < 3; j++) {
+            float d = b[3 * i] * b[3 * j] + b[3 * i + 1] * b[3 * j + 1] + b[3 * i + 2] * b[3 * j + 2];
+            if (fabsf(d - (i == j ? 1.0f : 0.0f)) > 1e-5f) return false;
+        }
+    return true;
+}
+
+// AUTO, TILE and PHASED apply to regular pyramids with spp 1..4 and an orthonormal
+// camera; anything else falls back to the per-lane walk.  All variants produce
+// identical bytes.
+int kernel_variant(const rt::RenderParams &p) {
+    const bool tile_ok = rt_tile_supported(p) && (!p.has_basis || orthonormal(p.basis));
+    switch (g_variant) {
+        case RT_VARIANT_LANE:
+            return RT_KERNEL_LANE;
+        case RT_VARIANT_WARP:
+            return RT_KERNEL_WARP;
+        case RT_VARIANT_TILE:
+            return tile_ok ? RT_KERNEL_TILE : RT_KERNEL_LANE;
+        default:
+            return tile_ok ? RT_KERNEL_PHASED : RT_KERNEL_LANE;
+    }
+}
+
+int tile_shape() {
+    static const char *force = getenv("RTRACE_TILE_SHAPE");  // kernel experiments
+    return (force && *force) ? atoi(force) : 0;
+}
+
+template <class T>
+int ensure_typed(T **buf, size_t *cap, size_t need_bytes) {
+    uint8_t *b = reinterpret_cast<uint8_t *>(*buf);
+    int rc = ensure(&b, cap, need_bytes);
+    *buf = reinterpret_cast<T *>(b);
+    return rc;
+}
+
+// Scratch of the PHASED variant for this stream (allocated on first use, grown on demand).
+int prepare_phased(rt_scene *s, rt::RenderParams &p, cudaStream_t stream) {
+    size_t wb = 0, hb = 0;
+    uint32_t units = 0;
+    rt_phased_scratch(p.width, p.row_count, p.spp, tile_shape(), &wb, &hb, &units);
+    std::lock_guard<std::mutex> lock(s->mu_phased);
+    rt_scene::Phased &ph = s->phased[stream];
+    int rc = ensure_typed(&ph.winner, &ph.winner_cap, wb);
+    if (rc == RT_OK) rc = ensure_typed(&ph.hdr, &ph.hdr_cap, hb);
+    if (rc == RT_OK && ph.pool_units < units) {
+        size_t cap = (size_t)ph.pool_units * sizeof(uint4);
+        rc = ensure_typed(&ph.pool, &cap, (size_t)units * sizeof(uint4));
+        if (rc == RT_OK) ph.pool_units = units;
+    }
+    if (rc == RT_OK && !ph.pool_count) CUDA_TRY(cudaMalloc(&ph.pool_count, sizeof(uint32_t)));
+    if (rc != RT_OK) return rc;
+    p.winner = ph.winner;
+    p.tile_hdr = ph.hdr;
+    p.pool = ph.pool;
+    p.pool_cap = ph.pool_units;
+    p.pool_count = ph.pool_count;
+    return RT_OK;
+}
+
+int launch(rt_scene *s, rt::RenderParams &p, bool diag, cudaStream_t stream) {
+    const int v = kernel_variant(p);
+    cudaError_t e;
+    if (v == RT_KERNEL_PHASED) {
+        int rc = prepare_phased(s, p, stream);
+        if (rc != RT_OK) return rc;
+        e = rt_launch_render_phased(diag, p, stream, tile_shape());
+    } else if (v == RT_KERNEL_TILE) {
+        e = rt_launch_render_tile(diag, p, stream, tile_shape());
+    } else {
+        e = rt_launch_render(v, diag, p, stream);
+    }
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
+    return RT_OK;
+}
+
+int launches_per_frame(const rt::RenderParams &p) { return kernel_variant(p) == RT_KERNEL_PHASED ? 4 : 1; }
+
 }  // namespace
 
 extern "C" {
@@ -217,7 +276,7 @@ int rt_set_device(int device) {
 }
 
 int rt_set_variant(int variant) {
-    if (variant < RT_VARIANT_AUTO || variant > RT_VARIANT_TILE) return fail(RT_ERR_INVALID, "unknown variant %d", variant);
+    if (variant < RT_VARIANT_AUTO || variant > RT_VARIANT_PHASED) return fail(RT_ERR_INVALID, "unknown variant %d", variant);
     g_variant = variant;
     return RT_OK;
 }
@@ -288,6 +347,12 @@ void rt_scene_destroy(rt_scene *s) {
         if (s->ev0) cudaEventDestroy(s->ev0);
         if (s->ev1) cudaEventDestroy(s->ev1);
         if (s->own_stream) cudaStreamDestroy(s->own_stream);
+        for (auto &kv : s->phased) {
+            if (kv.second.winner) cudaFree(kv.second.winner);
+            if (kv.second.hdr) cudaFree(kv.second.hdr);
+            if (kv.second.pool) cudaFree(kv.second.pool);
+            if (kv.second.pool_count) cudaFree(kv.second.pool_count);
+        }
     }
     delete s;
 }
@@ -403,7 +468,8 @@ static int render_rows_impl(rt_scene *s, const rt_camera *camera, uint32_t width
     }
 
     if (stats) CUDA_TRY(cudaEventRecord(s->ev0, stream));
-    CUDA_TRY(launch(p, diag, stream));
+    rc = launch(s, p, diag, stream);
+    if (rc != RT_OK) return rc;
     if (stats) CUDA_TRY(cudaEventRecord(s->ev1, stream));
 
     bool must_sync = false;
@@ -437,7 +503,7 @@ static int render_rows_impl(rt_scene *s, const rt_camera *camera, uint32_t width
         stats->total_ms = now_ms() - t0;
         stats->primary_rays = (uint64_t)width * row_count * spp * spp;
         stats->shadow_rays = counting ? ctr[1] : 0;
-        stats->kernel_launches = 1;
+        stats->kernel_launches = (uint32_t)launches_per_frame(p);
         stats->gpus = 1;
     }
     return RT_OK;
@@ -535,7 +601,10 @@ int rt_render_frame_multi(rt_scene *const *scenes, int ngpu, const rt_camera *ca
             p.pitch = row_bytes;
         }
         if (stats) CUDA_TRY(cudaEventRecord(s->ev0, s->own_stream));
-        CUDA_TRY(launch(p, false, s->own_stream));
+        {
+            int rc = launch(s, p, false, s->own_stream);
+            if (rc != RT_OK) return rc;
+        }
         if (stats) CUDA_TRY(cudaEventRecord(s->ev1, s->own_stream));
         if (g > 0)  // strided peer copy over NVLink: the pitch de-interleaves the band into the frame
             CUDA_TRY(cudaMemcpy2DAsync(frame + row_bytes * g, row_bytes * ngpu, s->d_fb, row_bytes, row_bytes, rows, cudaMemcpyDefault, s->own_stream));

@@ -90,6 +90,12 @@ struct RenderParams {
     uint32_t row_start, row_stride, row_count;  // image rows rendered by this launch
     uint8_t *out;                               // RGBA8, row j at out + j*pitch
     size_t pitch;
+    // PHASED variant scratch (L2-resident intermediates between the four launches)
+    uint4 *pool;            // candidate chunks, 16-byte units
+    uint32_t pool_cap;      // units
+    uint32_t *pool_count;   // units used (atomic)
+    uint4 *tile_hdr;        // per cull tile {primary chain, shadow chain, tmin bits, tmax bits}
+    uint32_t *winner;       // per sample: index of the closest leaf
     uint8_t *kinds;                    // optional per-sample classification
     unsigned long long *ray_counters;  // optional {primary_hits, shadow_rays}
 };

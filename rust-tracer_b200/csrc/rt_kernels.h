@@ -4,7 +4,7 @@
 #include <stddef.h>
 #include <stdint.h>
 
-enum { RT_KERNEL_LANE = 1, RT_KERNEL_WARP = 2, RT_KERNEL_TILE = 3 };
+enum { RT_KERNEL_LANE = 1, RT_KERNEL_WARP = 2, RT_KERNEL_TILE = 3, RT_KERNEL_PHASED = 4 };
 
 namespace rt {
 struct RenderParams;
@@ -20,3 +20,8 @@ bool rt_tile_supported(const rt::RenderParams &p);
 // shape 0: 16 ray slots per lane (largest tiles); shape 1: 4 slots per lane (4x more, shorter tiles)
 cudaError_t rt_launch_render_tile(bool diag, const rt::RenderParams &p, cudaStream_t stream, int shape);
 cudaError_t rt_launch_math_selftest(uint32_t n, uint32_t seed, unsigned long long *d_mismatch, cudaStream_t stream);
+
+// PHASED variant (rt_phased.cu): the TILE algorithm as four launches on one stream.
+void rt_phased_scratch(uint32_t width, uint32_t rows, uint32_t spp, int shape, size_t *winner_bytes, size_t *hdr_bytes,
+                       uint32_t *pool_units);
+cudaError_t rt_launch_render_phased(bool diag, const rt::RenderParams &p, cudaStream_t stream, int shape);

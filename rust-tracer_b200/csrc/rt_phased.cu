@@ -1,0 +1,552 @@
+// rt_phased.cu -- PHASED variant: the TILE algorithm as four homogeneous launches.
+//
+// The fused TILE kernel mixes two very different kinds of work in one CTA: the
+// hierarchy cull (one warp, a long dependent chain per step) and the per-sample
+// tests (every lane busy).  Warps waiting for a cull hold registers and hide no
+// latency.  Here each phase is its own launch on one stream, so every SM runs one
+// kind of work at full occupancy; intermediates are a few MB and stay in L2:
+//
+//   K1 cull_primary   one warp per CULL tile (CW x CH pixel tiles): walks the
+//                     skip-pointer hierarchy against the tile's cone, appends
+//                     candidate chunks {v = c - eye, v.v, r*r, index} to a pool.
+//   K2 test_primary   one warp per PIXEL tile: lane pre-filter + the reference's
+//                     exact f32 ray-sphere test (primitive.rs:55-72) over the
+//                     tile's candidates; writes the winner index per sample and
+//                     the tile's hit-distance range (atomicMin/Max).
+//   K3 cull_shadow    one warp per cull tile: shadow beam from that range, walk,
+//                     append shadow candidate chunks {c, r*r}.
+//   K4 shade_store    one warp per pixel tile: winner distance, normal, g, shadow
+//                     origin (render.rs:194-199), exact any-hit tests
+//                     (render.rs:202-208), accumulation in reference sample order,
+//                     RGBA8 quantisation, one framebuffer store per pixel.
+//
+// A cull tile whose candidates do not fit the pool is flagged and its pixel tiles
+// fall back to the per-lane walk (lane_traverse): the output never depends on the
+// pool size.  Exactness argument: see rt_tile.cu.
+#include "rt_cull.cuh"
+#include "rt_kernels.h"
+
+namespace rt {
+
+static constexpr uint32_t NO_CHUNK = 0xffffffffu;
+static constexpr uint32_t OVERFLOWED = 0xfffffffeu;
+static constexpr int P_WARPS = 4;  // warps per block in every phase (independent warps)
+
+struct CullShared {
+    float4 cand4[T_CAND];
+    float2 cand2[T_CAND];
+    uint32_t stack[T_STACK];
+};
+
+// Geometry shared by the four phases.
+template <int SPP, int PXW, int PXH, int CW, int CH>
+struct Geo {
+    static constexpr int NPX = PXW * PXH, NS = SPP * SPP, S = NPX * NS;
+    static constexpr float FRAC = (float)(SPP - 1) / (float)SPP;  // largest sub-sample offset
+    static constexpr int TW = 8 * PXW, TH = 4 * PXH;  // pixel tile (one warp)
+    static constexpr int BW = TW * CW, BH = TH * CH;  // cull tile
+    uint32_t ptiles_x, ptiles_y, ctiles_x, ctiles_y;
+    __host__ __device__ Geo(uint32_t width, uint32_t rows) {
+        ptiles_x = (width + TW - 1) / TW;
+        ptiles_y = (rows + TH - 1) / TH;
+        ctiles_x = (ptiles_x + CW - 1) / CW;
+        ctiles_y = (ptiles_y + CH - 1) / CH;
+    }
+    __host__ __device__ uint32_t n_ptiles() const { return ptiles_x * ptiles_y; }
+    __host__ __device__ uint32_t n_ctiles() const { return ctiles_x * ctiles_y; }
+};
+
+// Cone of a cull tile.
+template <class G>
+RT_DEV PrimaryBeam cull_tile_beam(const RenderParams &p, uint32_t ct_x, uint32_t ct_y) {
+    const float frac = G::FRAC;
+    const uint32_t x0 = ct_x * G::BW, j0 = ct_y * G::BH;
+    const uint32_t xh = min(x0 + G::BW, p.width) - 1u, jh = min(j0 + G::BH, p.row_count) - 1u;
+    const float ya = (float)(p.row_start + j0 * p.row_stride), yb = (float)(p.row_start + jh * p.row_stride);
+    return make_primary_beam(p, (float)x0, (float)xh + frac, fminf(ya, yb), fmaxf(ya, yb) + frac);
+}
+
+// Append the warp's candidate list (n records of UNITS 16-byte units) to the pool
+// as a chunk {count, next} + records, chained in front of `head`.
+template <int UNITS>
+RT_DEV uint32_t flush_chunk(const RenderParams &p, const CullShared &sm, int lane, uint32_t n, uint32_t head) {
+    if (n == 0 || head == OVERFLOWED) return head;
+    const uint32_t units = 1u + (uint32_t)UNITS * n;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(p.pool_count, units);
+    base = __shfl_sync(FULLMASK, base, 0);
+    if (base + units > p.pool_cap) return OVERFLOWED;
+    if (lane == 0) p.pool[base] = make_uint4(n, head, 0u, 0u);
+    for (uint32_t c = lane; c < n; c += 32) {
+        const float4 a = sm.cand4[c];
+        p.pool[base + 1u + UNITS * c] = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w));
+        if (UNITS == 2) {
+            const float2 e = sm.cand2[c];
+            p.pool[base + 2u + UNITS * c] = make_uint4(__float_as_uint(e.x), __float_as_uint(e.y), 0u, 0u);
+        }
+    }
+    return base;
+}
+
+// ---------------------------------------------------------------------------
+// K1: primary cull, one warp per cull tile
+// ---------------------------------------------------------------------------
+template <int SPP, int PXW, int PXH, int CW, int CH>
+__global__ void __launch_bounds__(32 * P_WARPS) phase_cull_primary(const RenderParams p) {
+    using G = Geo<SPP, PXW, PXH, CW, CH>;
+    __shared__ CullShared shared[P_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const G geo(p.width, p.row_count);
+    const uint32_t ct = blockIdx.x * P_WARPS + warp;
+    if (ct >= geo.n_ctiles()) return;
+    CullShared &sm = shared[warp];
+    const PrimaryBeam pb = cull_tile_beam<G>(p, ct % geo.ctiles_x, ct / geo.ctiles_x);
+    CullState cs;
+    cull_begin<true>(p, sm, pb, lane, cs);
+    uint32_t head = NO_CHUNK;
+    bool done;
+    do {
+        done = cull_run<true>(p, sm, pb, lane, cs);
+        head = flush_chunk<2>(p, sm, lane, cs.ncand, head);
+        __syncwarp();
+    } while (!done && head != OVERFLOWED);
+    if (lane == 0) p.tile_hdr[ct] = make_uint4(head, NO_CHUNK, 0x7f800000u, 0u);
+}
+
+// ---------------------------------------------------------------------------
+// K2: exact closest-hit tests, one warp per pixel tile
+// ---------------------------------------------------------------------------
+template <int SPP, int PXW, int PXH, int CW, int CH>
+__global__ void __launch_bounds__(32 * P_WARPS) phase_test_primary(const RenderParams p) {
+    using G = Geo<SPP, PXW, PXH, CW, CH>;
+    constexpr int S = G::S, NS = G::NS;
+    constexpr int GS = 2;  // slots processed together
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const G geo(p.width, p.row_count);
+    const uint32_t pt = blockIdx.x * P_WARPS + warp;
+    if (pt >= geo.n_ptiles()) return;
+    const uint32_t pt_x = pt % geo.ptiles_x, pt_y = pt / geo.ptiles_x;
+    const uint32_t ct = (pt_y / CH) * geo.ctiles_x + pt_x / CW;
+    const uint32_t tile_x0 = pt_x * G::TW, tile_j0 = pt_y * G::TH;
+    const V3 eye = v3(p.eye[0], p.eye[1], p.eye[2]);
+    uint32_t *winner = p.winner + (size_t)pt * S * 32;
+
+    uint32_t bx, bj;  // first pixel of this lane's block
+    slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, 0, bx, bj);
+    const bool lane_in = bx < p.width && bj < p.row_count;
+    const uint32_t head = p.tile_hdr[ct].x;
+    if (head == NO_CHUNK) return;  // no candidate at all: K4 sees an empty hit range and never reads the winners
+    float tmin = RT_INF, tmax = 0.0f;
+
+    if (head == OVERFLOWED) {  // pool exhausted for this cull tile: the per-lane walk (group.rs:72-83)
+        for (int s = 0; s < S; s++) {
+            uint32_t x, j;
+            slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s / NS, x, j);
+            uint32_t bi = NO_HIT;
+            if (x < p.width && j < p.row_count) {
+                const V3 d = slot_dir<SPP>(p, x, p.row_start + j * p.row_stride, s % NS);
+                float hitd = RT_INF;
+                lane_traverse<false>(p.sph, p.skip, p.n_nodes, eye, d, hitd, bi);
+                if (hitd == RT_INF) bi = NO_HIT;
+                else tmin = fminf(tmin, fabsf(hitd)), tmax = fmaxf(tmax, fabsf(hitd));
+            }
+            winner[s * 32 + lane] = bi;
+        }
+    } else {
+        // this lane's own block: a much narrower cone, used to pre-filter the tile's candidates
+        PrimaryBeam lb;
+        {
+            const float frac = (float)(SPP - 1) / (float)SPP;
+            const uint32_t xh = min(bx + PXW, p.width) - 1u, jh = min(bj + PXH, p.row_count) - 1u;
+            const float ya = (float)(p.row_start + bj * p.row_stride), yb = (float)(p.row_start + jh * p.row_stride);
+            lb = make_primary_beam(p, (float)bx, (float)xh + frac, fminf(ya, yb), fmaxf(ya, yb) + frac);
+        }
+        // the warp's pixel tile: between the cull tile's cone and the lane's
+        PrimaryBeam wb;
+        {
+            const float frac = (float)(SPP - 1) / (float)SPP;
+            const uint32_t xh = min(tile_x0 + G::TW, p.width) - 1u, jh = min(tile_j0 + G::TH, p.row_count) - 1u;
+            const float ya = (float)(p.row_start + tile_j0 * p.row_stride), yb = (float)(p.row_start + jh * p.row_stride);
+            wb = make_primary_beam(p, (float)tile_x0, (float)xh + frac, fminf(ya, yb), fmaxf(ya, yb) + frac);
+        }
+        // candidates c0..c1 (at most 32) of a chunk -> bit mask of those this LANE's block can see.
+        // First every lane tests ONE candidate against the warp tile's cone (ballot), then each lane
+        // tests the survivors against its own cone.
+        auto chunk_mask = [&](uint32_t base, uint32_t c0, uint32_t c1) {
+            bool w_ok = false;
+            if (c0 + lane < c1) {
+                const uint4 a = __ldg(&p.pool[base + 1u + 2u * (c0 + lane)]);
+                const uint4 e = __ldg(&p.pool[base + 2u + 2u * (c0 + lane)]);
+                const float4 af = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w));
+                w_ok = lane_test(wb, af, __uint_as_float(e.x));
+            }
+            uint32_t mask = 0;
+            for (uint32_t wm = __ballot_sync(FULLMASK, w_ok); wm; wm &= wm - 1u) {
+                const uint32_t c = c0 + (uint32_t)__ffs((int)wm) - 1u;
+                const uint4 a = __ldg(&p.pool[base + 1u + 2u * c]);
+                const uint4 e = __ldg(&p.pool[base + 2u + 2u * c]);
+                const float4 af = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w));
+                if (lane_in && lane_test(lb, af, __uint_as_float(e.x))) mask |= 1u << (c - c0);
+            }
+            return mask;
+        };
+        // mask of the first 32 candidates of the first chunk: reused by every slot group
+        uint32_t mask0 = 0;
+        if (head != NO_CHUNK) mask0 = chunk_mask(head, 0u, min(__ldg(&p.pool[head]).x, 32u));
+#pragma unroll 1
+        for (int s0 = 0; s0 < S; s0 += GS) {
+            V3 d[GS];
+            float bd[GS];
+            uint32_t bi[GS];
+#pragma unroll
+            for (int k = 0; k < GS; k++) {
+                const int s = (s0 + k < S) ? s0 + k : S - 1;
+                uint32_t x, j;
+                slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s / NS, x, j);
+                d[k] = slot_dir<SPP>(p, x, p.row_start + j * p.row_stride, s % NS);
+                bd[k] = RT_INF;
+                bi[k] = NO_HIT;
+            }
+            for (uint32_t base = head; base != NO_CHUNK;) {
+                const uint4 hdr = __ldg(&p.pool[base]);
+                const uint32_t n = hdr.x;
+                for (uint32_t c0 = 0; c0 < n; c0 += 32) {
+                    const uint32_t mask = (base == head && c0 == 0) ? mask0 : chunk_mask(base, c0, min(n, c0 + 32u));
+                    for (uint32_t m = mask; m; m &= m - 1u) {
+                        const uint32_t c = c0 + (uint32_t)__ffs((int)m) - 1u;
+                        const uint4 a = __ldg(&p.pool[base + 1u + 2u * c]);
+                        const uint4 e = __ldg(&p.pool[base + 2u + 2u * c]);
+                        const V3 v = v3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
+                        const uint32_t idx = e.y;
+#pragma unroll
+                        for (int k = 0; k < GS; k++) {
+                            const float dist = primary_distance(v, __uint_as_float(a.w), __uint_as_float(e.x), d[k]);
+                            // primitive.rs:79 + pre-order visiting: strictly closer wins, ties -> lowest index
+                            if (dist < bd[k] || (dist == bd[k] && idx < bi[k] && bi[k] != NO_HIT)) {
+                                bd[k] = dist;
+                                bi[k] = idx;
+                            }
+                        }
+                    }
+                }
+                base = hdr.y;
+            }
+#pragma unroll
+            for (int k = 0; k < GS; k++) {
+                if (s0 + k < S) {
+                    winner[(s0 + k) * 32 + lane] = bi[k];
+                    if (bi[k] != NO_HIT) {
+                        tmin = fminf(tmin, fabsf(bd[k]));
+                        tmax = fmaxf(tmax, fabsf(bd[k]));
+                    }
+                }
+            }
+        }
+    }
+    // hit-distance range of the cull tile (positive floats order as uints)
+    const uint32_t lo = __reduce_min_sync(FULLMASK, __float_as_uint(tmin));
+    const uint32_t hi = __reduce_max_sync(FULLMASK, __float_as_uint(tmax));
+    if (lane == 0 && lo != 0x7f800000u) {
+        uint32_t *h = reinterpret_cast<uint32_t *>(&p.tile_hdr[ct]);
+        atomicMin(h + 2, lo);
+        atomicMax(h + 3, hi);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K3: shadow cull, one warp per cull tile
+// ---------------------------------------------------------------------------
+template <int SPP, int PXW, int PXH, int CW, int CH>
+__global__ void __launch_bounds__(32 * P_WARPS) phase_cull_shadow(const RenderParams p) {
+    using G = Geo<SPP, PXW, PXH, CW, CH>;
+    __shared__ CullShared shared[P_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const G geo(p.width, p.row_count);
+    const uint32_t ct = blockIdx.x * P_WARPS + warp;
+    if (ct >= geo.n_ctiles()) return;
+    CullShared &sm = shared[warp];
+    const uint4 hdr = p.tile_hdr[ct];
+    if (hdr.z == 0x7f800000u || hdr.x == OVERFLOWED) {  // no hit in this tile / tile handled by the per-lane walk
+        if (lane == 0) reinterpret_cast<uint32_t *>(&p.tile_hdr[ct])[1] = hdr.x == OVERFLOWED ? OVERFLOWED : NO_CHUNK;
+        return;
+    }
+    const PrimaryBeam pb = cull_tile_beam<G>(p, ct % geo.ctiles_x, ct / geo.ctiles_x);
+    const V3 eye = v3(p.eye[0], p.eye[1], p.eye[2]);
+    ShadowBeam sb;
+    {
+        const float tlo = __uint_as_float(hdr.z), thi = __uint_as_float(hdr.w);
+        const float off = thi * 3.6e-4f + 1e-6f;  // |normal * distance * sqrt(eps)| <= distance * 3.4527e-4
+        float a0 = adiv(tlo, pb.secp) * 0.99999f - off;
+        float a1 = thi + off;
+        if (pb.wide) {  // no usable cone: origins anywhere within thi of the eye
+            a0 = 0.0f;
+            a1 = 0.0f;
+            sb.rho = thi * 1.001f + off;
+        } else {
+            sb.rho = thi * (pb.tanp + 3.6e-4f) * 1.001f + 1e-6f;
+        }
+        sb.none = false;
+        sb.px = fmaf(a0, pb.ax, eye.x), sb.py = fmaf(a0, pb.ay, eye.y), sb.pz = fmaf(a0, pb.az, eye.z);
+        sb.ax = pb.ax, sb.ay = pb.ay, sb.az = pb.az;
+        sb.lx = -p.light[0], sb.ly = -p.light[1], sb.lz = -p.light[2];  // render.rs:206
+        sb.len = a1 - a0;
+        float nx = sb.ay * sb.lz - sb.az * sb.ly, ny = sb.az * sb.lx - sb.ax * sb.lz, nz = sb.ax * sb.ly - sb.ay * sb.lx;
+        float sn = asqrt(nx * nx + ny * ny + nz * nz);
+        sb.degenerate = pb.wide || !(sn > 0.05f);
+        float isn = adiv(1.0f, fmaxf(sn, 1e-20f));
+        sb.nx = nx * isn, sb.ny = ny * isn, sb.nz = nz * isn;
+        sb.cosq = sb.ax * sb.lx + sb.ay * sb.ly + sb.az * sb.lz;
+        sb.inv_sin = isn * 1.00001f;
+        sb.inv_sin2 = isn * isn * 1.00001f;
+        sb.rmin = p.leaf_rmin;
+    }
+    CullState cs;
+    cull_begin<false>(p, sm, sb, lane, cs);
+    uint32_t head = NO_CHUNK;
+    bool done;
+    do {
+        done = cull_run<false>(p, sm, sb, lane, cs);
+        head = flush_chunk<1>(p, sm, lane, cs.ncand, head);
+        __syncwarp();
+    } while (!done && head != OVERFLOWED);
+    if (lane == 0) reinterpret_cast<uint32_t *>(&p.tile_hdr[ct])[1] = head;
+}
+
+// ---------------------------------------------------------------------------
+// K4: shading, shadow tests, accumulation, store; one warp per pixel tile
+// ---------------------------------------------------------------------------
+template <int SPP, int PXW, int PXH, int CW, int CH, bool DIAG>
+__global__ void __launch_bounds__(32 * P_WARPS) phase_shade_store(const RenderParams p) {
+    using G = Geo<SPP, PXW, PXH, CW, CH>;
+    constexpr int S = G::S, NS = G::NS;
+    constexpr int GS = 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const G geo(p.width, p.row_count);
+    const uint32_t pt = blockIdx.x * P_WARPS + warp;
+    if (pt >= geo.n_ptiles()) return;
+    const uint32_t pt_x = pt % geo.ptiles_x, pt_y = pt / geo.ptiles_x;
+    const uint32_t ct = (pt_y / CH) * geo.ctiles_x + pt_x / CW;
+    const uint32_t tile_x0 = pt_x * G::TW, tile_j0 = pt_y * G::TH;
+    const uint32_t *winner = p.winner + (size_t)pt * S * 32;
+
+    const V3 eye = v3(p.eye[0], p.eye[1], p.eye[2]);
+    const V3 light = v3(p.light[0], p.light[1], p.light[2]);
+    const V3 to_light = vmulf(light, -1.0f);  // render.rs:206
+    // render.rs:172-186, :199 -- constants folded at compile time in IEEE f32
+    constexpr float OBJ_R = 174.0f / 255.0f, OBJ_G = 49.0f / 255.0f, BG_R = 34.0f / 255.0f, BG_G = 10.0f / 255.0f;
+    const V3 K_object = v3(OBJ_R, OBJ_G, OBJ_G), K_background = v3(BG_R, BG_G, BG_G);
+    const V3 K_ambient = v3(fmul(BG_R, 0.8f), fmul(BG_G, 0.8f), fmul(BG_G, 0.8f));
+    const float sqrt_eps = __uint_as_float(0x39b504f3u);       // sqrt(f32::EPSILON) = 3.4526698e-4
+    const float recip = frecip(fmul((float)SPP, (float)SPP));  // render.rs:219-220
+
+    uint32_t bx, bj;
+    slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, 0, bx, bj);
+    const bool lane_in = bx < p.width && bj < p.row_count;
+    const uint4 tile_hdr = p.tile_hdr[ct];
+    const uint32_t head = tile_hdr.y;
+    unsigned n_hits = 0, n_shadow = 0;
+    V3 c = v3(0.0f, 0.0f, 0.0f);  // colour / alpha of the pixel being accumulated (render.rs:233-234)
+    float alpha = 0.0f;
+    if (tile_hdr.z == 0x7f800000u) {
+        // no ray of this cull tile hit anything: every sample adds BACKGROUND (render.rs:190-193)
+        if (lane_in) {
+            for (int smp = 0; smp < NS; smp++) c = vadd(c, K_background);
+            const V3 q = vmulf(c, recip);
+            const uint32_t px = scale_u8_fast(q.x) | (scale_u8_fast(q.y) << 8) | (scale_u8_fast(q.z) << 16) |
+                                (scale_u8_fast(fmul(0.0f, recip)) << 24);
+            for (int pi = 0; pi < G::NPX; pi++) {
+                uint32_t x, j;
+                slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, pi, x, j);
+                if (x < p.width && j < p.row_count) {
+                    *reinterpret_cast<uint32_t *>(p.out + (size_t)j * p.pitch + (size_t)x * 4) = px;
+                    if (DIAG && p.kinds)
+                        for (int smp = 0; smp < NS; smp++) p.kinds[((size_t)j * p.width + x) * NS + smp] = K_BACKGROUND;
+                }
+            }
+        }
+    } else if (lane_in) {
+#pragma unroll 1
+        for (int s0 = 0; s0 < S; s0 += GS) {
+            V3 o[GS];
+            float g[GS];
+            uint32_t pend = 0;  // bit k: slot s0+k casts a shadow ray that is still unoccluded
+            uint32_t occluded = 0;
+#pragma unroll
+            for (int k = 0; k < GS; k++) {
+                const int s = (s0 + k < S) ? s0 + k : S - 1;
+                uint32_t x, j;
+                slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s / NS, x, j);
+                const V3 d = slot_dir<SPP>(p, x, p.row_start + j * p.row_stride, s % NS);
+                const uint32_t wi = winner[s * 32 + lane];
+                const bool hit = wi != NO_HIT;
+                const float4 w = __ldg(&p.sph[hit ? wi : 0u]);
+                const V3 v = vsub(v3(w.x, w.y, w.z), eye);
+                const float dist = hit ? primary_distance(v, vdot(v, v), fmul(w.w, w.w), d) : 1.0f;
+                // primitive.rs:83 normal; render.rs:194 g; render.rs:199 shadow origin
+                const V3 nrm = vnormalized_nr(vadd(eye, vsub(vmulf(d, dist), v3(w.x, w.y, w.z))));
+                const float gg = vdot(nrm, light);
+                o[k] = vadd(vadd(eye, vmulf(d, dist)), vmulf(nrm, fmul(dist, sqrt_eps)));
+                g[k] = hit ? gg : RT_INF;
+                if (hit && !(gg >= 0.0f) && s0 + k < S) pend |= 1u << k;
+            }
+            if (head == OVERFLOWED) {  // per-lane walk, any-hit (render.rs:202-208)
+#pragma unroll
+                for (int k = 0; k < GS; k++) {
+                    if ((pend >> k) & 1u) {
+                        float sh = RT_INF;
+                        uint32_t dummy = 0;
+                        lane_traverse<true>(p.sph, p.skip, p.n_nodes, o[k], to_light, sh, dummy);
+                        if (sh != RT_INF) occluded |= 1u << k;
+                    }
+                }
+                pend = 0;
+            }
+            for (uint32_t base = head; base < OVERFLOWED && pend;) {
+                const uint4 hdr = __ldg(&p.pool[base]);
+                for (uint32_t ci = 0; ci < hdr.x && pend; ci++) {
+                    const uint4 au = __ldg(&p.pool[base + 1u + ci]);
+                    const V3 cc = v3(__uint_as_float(au.x), __uint_as_float(au.y), __uint_as_float(au.z));
+#pragma unroll
+                    for (int k = 0; k < GS; k++) {
+                        // primitive.rs:56-58 for the shadow ray {pos: o, dir: -light}
+                        const V3 v = vsub(cc, o[k]);
+                        const float b = vdot(v, to_light);
+                        const float disc = fadd(fsub(fmul(b, b), vdot(v, v)), __uint_as_float(au.w));
+                        // finite iff disc >= 0 and !(b + sqrt(disc) < 0) (primitive.rs:60-68); b >= 0 settles the latter
+                        bool f = !(disc < 0.0f);
+                        if (f && b < 0.0f) f = !(fadd(b, fsqrt_nr(disc)) < 0.0f);
+                        if (f && ((pend >> k) & 1u)) {
+                            pend &= ~(1u << k);
+                            occluded |= 1u << k;
+                        }
+                    }
+                }
+                base = hdr.y;
+            }
+            // accumulate in reference sample order (render.rs:236-250), quantise, store (render.rs:92-109)
+#pragma unroll
+            for (int k = 0; k < GS; k++) {
+                const int s = s0 + k;
+                if (s < S) {
+                    const int pi = s / NS, smp = s % NS;
+                    uint32_t x, j;
+                    slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, pi, x, j);
+                    const bool inside = x < p.width && j < p.row_count;
+                    if (smp == 0) {
+                        c = v3(0.0f, 0.0f, 0.0f);
+                        alpha = 0.0f;
+                    }
+                    uint8_t kind;
+                    if (g[k] == RT_INF) {  // render.rs:190-193
+                        c = vadd(c, K_background);
+                        kind = K_BACKGROUND;
+                    } else if (g[k] >= 0.0f) {  // render.rs:195-198
+                        c = vadd(c, K_ambient);
+                        kind = K_AWAY;
+                        if (DIAG && inside) n_hits++;
+                    } else {
+                        if (DIAG && inside) n_hits++, n_shadow++;
+                        const float ng = -g[k];
+                        if (!((occluded >> k) & 1u)) {  // render.rs:208-210
+                            c = vadd(vadd(c, vmulf(K_object, ng)), K_ambient);
+                            alpha = fadd(alpha, 1.0f);
+                            kind = K_LIT;
+                        } else {  // render.rs:211-214
+                            c = vadd(vadd(c, K_background), vmulf(K_ambient, ng));
+                            kind = K_SHADOWED;
+                        }
+                    }
+                    if (DIAG && p.kinds && inside) p.kinds[((size_t)j * p.width + x) * NS + smp] = kind;
+                    if (smp == NS - 1 && inside) {
+                        const V3 q = vmulf(c, recip);
+                        const float al = fmul(alpha, recip);
+                        const uint32_t px = scale_u8_fast(q.x) | (scale_u8_fast(q.y) << 8) |
+                                            (scale_u8_fast(q.z) << 16) | (scale_u8_fast(al) << 24);
+                        *reinterpret_cast<uint32_t *>(p.out + (size_t)j * p.pitch + (size_t)x * 4) = px;
+                    }
+                }
+            }
+        }
+    }
+    if (DIAG && p.ray_counters) {
+        n_hits = __reduce_add_sync(FULLMASK, n_hits);
+        n_shadow = __reduce_add_sync(FULLMASK, n_shadow);
+        if (lane == 0) {
+            atomicAdd(&p.ray_counters[0], (unsigned long long)n_hits);
+            atomicAdd(&p.ray_counters[1], (unsigned long long)n_shadow);
+        }
+    }
+}
+
+}  // namespace rt
+
+using namespace rt;
+
+template <int SPP, int PXW, int PXH, int CW, int CH>
+static cudaError_t launch_phased(bool diag, const RenderParams &p, cudaStream_t stream) {
+    using G = Geo<SPP, PXW, PXH, CW, CH>;
+    const G geo(p.width, p.row_count);
+    const uint32_t nc = geo.n_ctiles(), np = geo.n_ptiles();
+    if (nc == 0 || np == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(p.pool_count, 0, sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+    const unsigned cb = (nc + P_WARPS - 1) / P_WARPS, pb = (np + P_WARPS - 1) / P_WARPS;
+    phase_cull_primary<SPP, PXW, PXH, CW, CH><<<cb, 32 * P_WARPS, 0, stream>>>(p);
+    phase_test_primary<SPP, PXW, PXH, CW, CH><<<pb, 32 * P_WARPS, 0, stream>>>(p);
+    phase_cull_shadow<SPP, PXW, PXH, CW, CH><<<cb, 32 * P_WARPS, 0, stream>>>(p);
+    if (diag)
+        phase_shade_store<SPP, PXW, PXH, CW, CH, true><<<pb, 32 * P_WARPS, 0, stream>>>(p);
+    else
+        phase_shade_store<SPP, PXW, PXH, CW, CH, false><<<pb, 32 * P_WARPS, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// Scratch the phased pipeline needs for a frame of `rows` x `width`, `spp`: winner
+// indices (4 B per padded sample), tile headers (16 B per cull tile) and the
+// candidate pool (16 B units).
+void rt_phased_scratch(uint32_t width, uint32_t rows, uint32_t spp, int shape, size_t *winner_bytes, size_t *hdr_bytes,
+                       uint32_t *pool_units) {
+    uint32_t nc = 0, np = 0, S = 0;
+#define RT_GEO(SPP, PXW, PXH, CW, CH)                     \
+    {                                                     \
+        Geo<SPP, PXW, PXH, CW, CH> g(width, rows);        \
+        nc = g.n_ctiles(), np = g.n_ptiles(), S = g.S;    \
+    }
+    switch (spp) {
+        case 1:
+            if (shape == 1) RT_GEO(1, 2, 2, 4, 4) else RT_GEO(1, 2, 2, 2, 2)
+            break;
+        case 2:
+            if (shape == 1) RT_GEO(2, 1, 1, 4, 4) else RT_GEO(2, 1, 1, 2, 2)
+            break;
+        case 3:
+            RT_GEO(3, 1, 1, 2, 2)
+            break;
+        default:
+            if (shape == 1) RT_GEO(4, 1, 1, 4, 4) else RT_GEO(4, 1, 1, 2, 2)
+            break;
+    }
+#undef RT_GEO
+    *winner_bytes = (size_t)np * S * 32 * sizeof(uint32_t);
+    *hdr_bytes = (size_t)nc * sizeof(uint4);
+    uint64_t units = (uint64_t)nc * 256u;
+    if (units < (1u << 20)) units = 1u << 20;
+    if (units > (1u << 26)) units = 1u << 26;  // 1 GiB of 16-byte units
+    *pool_units = (uint32_t)units;
+}
+
+cudaError_t rt_launch_render_phased(bool diag, const RenderParams &p, cudaStream_t stream, int shape) {
+    // shape 0: cull tile = 2x2 pixel tiles; shape 1: 4x4 pixel tiles
+    switch (p.spp) {
+        case 1:
+            return shape == 1 ? launch_phased<1, 2, 2, 4, 4>(diag, p, stream) : launch_phased<1, 2, 2, 2, 2>(diag, p, stream);
+        case 2:
+            return shape == 1 ? launch_phased<2, 1, 1, 4, 4>(diag, p, stream) : launch_phased<2, 1, 1, 2, 2>(diag, p, stream);
+        case 3:
+            return launch_phased<3, 1, 1, 2, 2>(diag, p, stream);
+        case 4:
+            return shape == 1 ? launch_phased<4, 1, 1, 4, 4>(diag, p, stream) : launch_phased<4, 1, 1, 2, 2>(diag, p, stream);
+        default:
+            return cudaErrorInvalidValue;
+    }
+}
