@@ -219,6 +219,10 @@ def main():
     gathered = [torch.zeros_like(fb) for _ in range(world)] if (bands and rank == 0) else None
     frame = torch.zeros((max_rows * world, width, 4), dtype=torch.uint8, device="cuda") if (bands and rank == 0) else None
 
+    # kernels launched per step (the PHASED variant is four launches per frame)
+    _, st0 = rt.Renderer.render_rows(opts, scene, row_start=row_start, row_stride=row_stride, row_count=my_rows,
+                                     out_ptr=fb.data_ptr(), stream=stream.cuda_stream, want_stats=True)
+    launches_per_step = int(st0.kernel_launches)
     # rays of this rank's share of a step, counted on the device the way the reference's work is counted
     primary, shadow = scene.count_rays(width, height, spp, row_start, row_stride, my_rows)
     rays_rank = primary + shadow
@@ -257,17 +261,30 @@ def main():
     wall_ms = (time.perf_counter() - w0) * 1e3
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
 
-    # ---- e2e: the C-ABI call a user makes, host buffer out, every step ------------------------
-    pinned = rt.PinnedBuffer(max(my_rows, 1) * width * 4)
-    e2e_steps = max(5, min(args.steps, 50))
-    for _ in range(2):
-        rt.Renderer.render_rows(opts, scene, row_start=row_start, row_stride=row_stride, row_count=my_rows,
-                                out_ptr=pinned.ptr)
+    # ---- e2e: the C-ABI call a user makes, every frame delivered to HOST memory ----------------
+    # frames mode: rt_render_sweep (what `rtrace --frames` calls): the device-to-host copy of frame f
+    # overlaps the render of frame f+1; the callback sees every frame in pinned host memory.
+    # bands mode: rt_render_rows into a pinned host buffer, synchronously.
+    e2e_steps = max(5, min(args.steps, 100))
+    seen = []
+
+    def on_frame(f, arr):
+        seen.append(int(arr[0, 0, 0]))   # touch the host copy of every frame
+
+    pinned = rt.PinnedBuffer(max(my_rows, 1) * width * 4) if bands else None
+
+    def e2e_run(n):
+        if bands:
+            for _ in range(n):
+                rt.Renderer.render_rows(opts, scene, row_start=row_start, row_stride=row_stride, row_count=my_rows,
+                                        out_ptr=pinned.ptr)
+        else:
+            rt.Renderer.render_sweep(opts, scene, n, on_frame=on_frame)
+
+    e2e_run(3)
     barrier()
     e0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        rt.Renderer.render_rows(opts, scene, row_start=row_start, row_stride=row_stride, row_count=my_rows,
-                                out_ptr=pinned.ptr)   # returns after the frame is in host memory
+    e2e_run(e2e_steps)
     barrier()
     e2e_ms = (time.perf_counter() - e0) * 1e3
     t_end = time.time()
@@ -332,10 +349,12 @@ def main():
                         "frac": fb_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
                         "note": "algorithmic HBM bytes = framebuffer written once (4 B/pixel); peak = MEASURED_PEAKS.json hbm_gbs" if peaks else "peak = fallback 6.65 TB/s"},
             },
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 256,
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 512,
                     "d2h_bytes_per_step": fb_bytes, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                    "note": "rt_render_rows -> pinned host buffer: kernel-parameter block (camera, options) in, RGBA8 frame out"},
-            "gpu_launches": args.steps * world,
+                    "note": ("rt_render_rows -> pinned host buffer, synchronous" if bands else
+                             "rt_render_sweep: per frame the kernel-parameter blocks (camera, options; 4 launches) go in "
+                             "and the RGBA8 frame comes out to pinned host memory; copy of frame f overlaps render of f+1")},
+            "gpu_launches": args.steps * world * launches_per_step,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

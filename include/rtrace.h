@@ -139,6 +139,16 @@ int rt_render_frame(const rt_scene *s, const rt_camera *camera,
                     uint32_t width, uint32_t height, uint32_t spp,
                     uint8_t *rgba_out, size_t rgba_len, rt_stats *stats);
 
+/* A sweep of n_frames frames (cameras[f], or the reference camera when cameras is
+ * NULL) with the device-to-host copy of frame f overlapping the render of frame
+ * f+1.  `cb` is called on the calling thread, in frame order, with a pinned host
+ * buffer that stays valid until the callback returns.  This is the end-to-end
+ * path of the orbit sweep (BASELINE C5) and what `rtrace --frames` uses. */
+typedef void (*rt_frame_callback)(void *user, uint32_t frame, const uint8_t *rgba, size_t len);
+int rt_render_sweep(const rt_scene *s, const rt_camera *cameras, uint32_t n_frames,
+                    uint32_t width, uint32_t height, uint32_t spp,
+                    rt_frame_callback cb, void *user, rt_stats *stats);
+
 /* Whole frame on ngpu GPUs of this process (devices 0..ngpu-1): the scene is
  * replicated, rows are interleaved (GPU g renders rows g, g+ngpu, ...) and the
  * bands are gathered into GPU 0's frame by strided peer copies over NVLink, then

@@ -51,6 +51,12 @@ struct rt_scene {
         uint32_t pool_units = 0;
         uint32_t *pool_count = nullptr;
     };
+    // rt_render_sweep: double-buffered frames and the copy stream
+    uint8_t *sweep_dev[2] = {nullptr, nullptr};
+    uint8_t *sweep_host[2] = {nullptr, nullptr};
+    size_t sweep_bytes = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t sweep_rendered[2] = {nullptr, nullptr}, sweep_copied[2] = {nullptr, nullptr};
     std::map<cudaStream_t, Phased> phased;
     std::mutex mu_phased;  // guards the map only (mu may already be held by the caller)
 };
@@ -138,6 +144,7 @@ void fill_params(const rt_scene *s, const rt_camera *cam, uint32_t w, uint32_t h
     p.n_nodes = s->n;
     p.level = s->flat.level;
     p.leaf_rmin = s->flat.leaf_rmin;
+    for (int k = 0; k < 3; k++) p.scene_center[k] = s->flat.sph.empty() ? 0.0f : s->flat.sph[k];
     const float *eye = cam ? cam->eye : s->flat.eye;
     for (int k = 0; k < 3; k++) {
         p.eye[k] = eye[k];
@@ -193,9 +200,24 @@ int kernel_variant(const rt::RenderParams &p) {
             return RT_KERNEL_WARP;
         case RT_VARIANT_TILE:
             return tile_ok ? RT_KERNEL_TILE : RT_KERNEL_LANE;
-        default:
+        case RT_VARIANT_PHASED:
             return tile_ok ? RT_KERNEL_PHASED : RT_KERNEL_LANE;
+        default:
+            break;
     }
+    if (!tile_ok) return RT_KERNEL_LANE;
+    // AUTO (measured on B200, profiles/r01_variant_matrix.json):
+    //  * when the smallest leaves project to less than ~2.5 sample spacings the exact test is
+    //    rounding noise, the cull must inflate them several-fold and the per-lane
+    //    walk, which needs no inflation, wins;
+    //  * frames with few pixel tiles cannot fill the GPU four times over: the fused kernel wins;
+    //  * otherwise the four homogeneous launches win.
+    const float dx = p.eye[0] - p.scene_center[0], dy = p.eye[1] - p.scene_center[1], dz = p.eye[2] - p.scene_center[2];
+    const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+    const float leaf_px = p.leaf_rmin * (float)p.width / fmaxf(dist, 1e-6f) * (float)p.spp;
+    if (leaf_px < 2.5f) return RT_KERNEL_LANE;
+    const uint64_t pixel_tiles = (uint64_t)p.width * p.row_count / (p.spp == 1 ? 128u : 32u);  // one warp each
+    return pixel_tiles < 40000 ? RT_KERNEL_TILE : RT_KERNEL_PHASED;
 }
 
 int tile_shape() {
@@ -347,6 +369,13 @@ void rt_scene_destroy(rt_scene *s) {
         if (s->ev0) cudaEventDestroy(s->ev0);
         if (s->ev1) cudaEventDestroy(s->ev1);
         if (s->own_stream) cudaStreamDestroy(s->own_stream);
+        for (int k = 0; k < 2; k++) {
+            if (s->sweep_dev[k]) cudaFree(s->sweep_dev[k]);
+            if (s->sweep_host[k]) cudaFreeHost(s->sweep_host[k]);
+            if (s->sweep_rendered[k]) cudaEventDestroy(s->sweep_rendered[k]);
+            if (s->sweep_copied[k]) cudaEventDestroy(s->sweep_copied[k]);
+        }
+        if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
         for (auto &kv : s->phased) {
             if (kv.second.winner) cudaFree(kv.second.winner);
             if (kv.second.hdr) cudaFree(kv.second.hdr);
@@ -547,6 +576,71 @@ int rt_render_frame(const rt_scene *s, const rt_camera *camera, uint32_t width, 
     if (rgba_len < (size_t)width * height * 4) return fail(RT_ERR_BUFFER, "rgba_out holds %zu bytes, frame needs %zu", rgba_len, (size_t)width * height * 4);
     return render_rows_impl(const_cast<rt_scene *>(s), camera, width, height, spp, 0, 1, height, rgba_out, 0, nullptr,
                             nullptr, stats, nullptr, nullptr);
+}
+
+int rt_render_sweep(const rt_scene *cs, const rt_camera *cameras, uint32_t n_frames, uint32_t width, uint32_t height,
+                    uint32_t spp, rt_frame_callback cb, void *user, rt_stats *stats) {
+    rt_scene *s = const_cast<rt_scene *>(cs);
+    int rc = check_frame_args(s, width, height, spp, 0, 1, height);
+    if (rc != RT_OK) return rc;
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (n_frames == 0) return RT_OK;
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(RT_ERR_CUDA, "cannot select device %d", s->device);
+    std::lock_guard<std::mutex> lock(s->mu);
+    const double t0 = now_ms();
+    const size_t row_bytes = (size_t)width * 4, frame_bytes = row_bytes * height;
+    // two device frames + two pinned host frames: the copy of frame f overlaps the render of f+1
+    if (s->sweep_bytes < frame_bytes) {
+        for (int k = 0; k < 2; k++) {
+            if (s->sweep_dev[k]) cudaFree(s->sweep_dev[k]);
+            if (s->sweep_host[k]) cudaFreeHost(s->sweep_host[k]);
+            s->sweep_dev[k] = s->sweep_host[k] = nullptr;
+        }
+        s->sweep_bytes = 0;
+        for (int k = 0; k < 2; k++) {
+            CUDA_TRY(cudaMalloc(&s->sweep_dev[k], frame_bytes));
+            CUDA_TRY(cudaHostAlloc((void **)&s->sweep_host[k], frame_bytes, cudaHostAllocPortable));
+        }
+        s->sweep_bytes = frame_bytes;
+    }
+    if (!s->copy_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; k++) {
+            CUDA_TRY(cudaEventCreateWithFlags(&s->sweep_rendered[k], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&s->sweep_copied[k], cudaEventDisableTiming));
+        }
+    }
+    uint32_t launches = 0;
+    for (uint32_t f = 0; f <= n_frames; f++) {
+        if (f < n_frames) {
+            const int k = (int)(f & 1u);
+            rt::RenderParams p;
+            fill_params(s, cameras ? &cameras[f] : nullptr, width, height, spp, 0, 1, height, p);
+            p.out = s->sweep_dev[k];
+            p.pitch = row_bytes;
+            if (f >= 2) CUDA_TRY(cudaStreamWaitEvent(s->own_stream, s->sweep_copied[k], 0));  // frame f-2 has left this buffer
+            rc = launch(s, p, false, s->own_stream);
+            if (rc != RT_OK) return rc;
+            launches += (uint32_t)launches_per_frame(p);
+            CUDA_TRY(cudaEventRecord(s->sweep_rendered[k], s->own_stream));
+            CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->sweep_rendered[k], 0));
+            CUDA_TRY(cudaMemcpyAsync(s->sweep_host[k], s->sweep_dev[k], frame_bytes, cudaMemcpyDeviceToHost, s->copy_stream));
+            CUDA_TRY(cudaEventRecord(s->sweep_copied[k], s->copy_stream));
+        }
+        if (f >= 1) {  // hand frame f-1 to the caller while frame f renders
+            const int k = (int)((f - 1) & 1u);
+            CUDA_TRY(cudaEventSynchronize(s->sweep_copied[k]));
+            if (cb) cb(user, f - 1, s->sweep_host[k], frame_bytes);
+        }
+    }
+    if (stats) {
+        stats->total_ms = now_ms() - t0;
+        stats->primary_rays = (uint64_t)width * height * spp * spp * n_frames;
+        stats->kernel_launches = launches;
+        stats->gpus = 1;
+    }
+    return RT_OK;
 }
 
 int rt_render_frame_multi(rt_scene *const *scenes, int ngpu, const rt_camera *camera, uint32_t width, uint32_t height,

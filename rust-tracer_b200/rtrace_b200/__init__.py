@@ -22,7 +22,8 @@ ABI_SYMBOLS = [
     "rt_last_error", "rt_version", "rt_device_count", "rt_set_device", "rt_set_variant",
     "rt_scene_create", "rt_scene_create_default", "rt_scene_create_from_nodes", "rt_scene_destroy",
     "rt_scene_counts", "rt_scene_export_nodes", "rt_flatten_pyramid_host", "rt_scene_light", "rt_scene_eye",
-    "rt_scene_device", "rt_render_region", "rt_render_rows", "rt_render_frame", "rt_render_frame_multi",
+    "rt_scene_device", "rt_render_region", "rt_render_rows", "rt_render_frame", "rt_render_sweep",
+    "rt_render_frame_multi",
     "rt_count_rays", "rt_trace_rays", "rt_measure_fp32_peak", "rt_microbench_fp32", "rt_selftest_math", "rt_host_alloc", "rt_host_free",
 ]
 
@@ -41,6 +42,8 @@ class Stats(C.Structure):
     _fields_ = [("primary_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("kernel_ms", C.c_double),
                 ("total_ms", C.c_double), ("kernel_launches", C.c_uint32), ("gpus", C.c_uint32)]
 
+
+FRAME_CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint8), C.c_size_t)
 
 _lib = None
 
@@ -75,6 +78,7 @@ def lib():
     L.rt_render_rows.argtypes = [vp, C.POINTER(Camera), u32, u32, u32, u32, u32, u32, u8p, C.c_size_t, u8p, vp,
                                  C.POINTER(Stats)]
     L.rt_render_frame.argtypes = [vp, C.POINTER(Camera), u32, u32, u32, u8p, C.c_size_t, C.POINTER(Stats)]
+    L.rt_render_sweep.argtypes = [vp, C.POINTER(Camera), u32, u32, u32, u32, FRAME_CALLBACK, vp, C.POINTER(Stats)]
     L.rt_render_frame_multi.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(Camera), u32, u32, u32, u8p, C.c_size_t,
                                         C.POINTER(Stats)]
     L.rt_count_rays.argtypes = [vp, C.POINTER(Camera), u32, u32, u32, u32, u32, u32, u64p, u64p]
@@ -287,6 +291,23 @@ class Renderer:
         _check(lib().rt_render_frame(scene.handle, C.byref(camera) if camera is not None else None, w, h, spp,
                                      out_ptr, w * h * 4, C.byref(st) if st is not None else None))
         return (out, st) if want_stats else out
+
+    @staticmethod
+    def render_sweep(options, scene, n_frames, cameras=None, on_frame=None):
+        """n_frames frames, copy of frame f overlapping the render of f+1; on_frame(f, array) per frame."""
+        w, h, spp = options.width, options.height, options.samples_per_pixel
+        cams = None
+        if cameras is not None:
+            cams = (Camera * n_frames)(*cameras)
+
+        def _cb(user, frame, ptr, nbytes):
+            if on_frame is not None:
+                on_frame(int(frame), np.ctypeslib.as_array(ptr, shape=(h, w, 4)))
+
+        cb = FRAME_CALLBACK(_cb)
+        st = Stats()
+        _check(lib().rt_render_sweep(scene.handle, cams, n_frames, w, h, spp, cb, None, C.byref(st)))
+        return st
 
     @staticmethod
     def render_multi(options, scenes, camera=None, want_stats=False):

@@ -172,3 +172,34 @@ def test_full_size_properties_c3(rt, oracle):
     for y in rows:
         ref, _ = os_.render_rows(w, h, spp, y, 1, 1)
         assert_same(full[y:y + 1], ref, "row %d" % y)
+
+
+def test_sweep_delivers_every_frame_in_order(rt, oracle, gpu_scene8, oracle_scene8):
+    """rt_render_sweep: double-buffered frames, each equal to the oracle's frame for that camera."""
+    w, h, spp, n = 160, 90, 1, 5
+    cams = [rt.orbit_camera(f, 40) for f in range(n)]
+    got = {}
+    st = rt.Renderer.render_sweep(rt.RenderOptions(w, h, spp), gpu_scene8, n, cameras=cams,
+                                  on_frame=lambda f, a: got.__setitem__(f, a.copy()))
+    assert sorted(got) == list(range(n)) and st.primary_rays == w * h * n
+    for f in range(n):
+        oc = oracle.Camera()
+        for k in ("eye", "right", "up", "forward"):
+            getattr(oc, k)[:] = getattr(cams[f], k)[:]
+        ref, _ = oracle_scene8.render(w, h, spp, camera=oc)
+        assert_same(got[f], ref, "sweep frame %d" % f)
+    # reference camera when no cameras are given
+    got.clear()
+    rt.Renderer.render_sweep(rt.RenderOptions(w, h, spp), gpu_scene8, 3, on_frame=lambda f, a: got.__setitem__(f, a.copy()))
+    base, _ = oracle_scene8.render(w, h, spp)
+    assert all(np.array_equal(got[f], base) for f in range(3))
+
+
+def test_auto_picks_a_variant_for_every_regime(rt, oracle):
+    """AUTO's three regimes (noise-limited leaves -> LANE, small frame -> TILE, large -> PHASED) all match the oracle."""
+    for (w, h, spp, level) in [(640, 360, 1, 10), (640, 360, 2, 8), (2560, 1440, 1, 8)]:
+        gs, os_ = rt.Scene(level=level), oracle.Scene(level=level)
+        rt.set_variant(rt.VARIANT_AUTO)
+        img = rt.Renderer.render(rt.RenderOptions(w, h, spp), gs)
+        ref, _ = os_.render(w, h, spp)
+        assert_same(img, ref, "auto %dx%d spp %d L%d" % (w, h, spp, level))
