@@ -209,15 +209,15 @@ def main():
     opts = rt.RenderOptions(width, height, spp)
     stream = torch.cuda.current_stream()
     bands = args.mode == "bands" and world > 1
+    from rtrace_b200 import partition
     if bands:
-        my_rows = (height - rank + world - 1) // world if height > rank else 0
-        max_rows = (height + world - 1) // world
-        row_start, row_stride = rank, world
+        row_start, row_stride, my_rows = partition.band_spec(height, rank, world)
+        max_rows = partition.band_capacity(height, world)
     else:
         my_rows, max_rows, row_start, row_stride = height, height, 0, 1
     fb = torch.zeros((max_rows, width, 4), dtype=torch.uint8, device="cuda")
     gathered = [torch.zeros_like(fb) for _ in range(world)] if (bands and rank == 0) else None
-    frame = torch.zeros((max_rows * world, width, 4), dtype=torch.uint8, device="cuda") if (bands and rank == 0) else None
+    frame_box = [None]
 
     # kernels launched per step (the PHASED variant is four launches per frame)
     _, st0 = rt.Renderer.render_rows(opts, scene, row_start=row_start, row_stride=row_stride, row_count=my_rows,
@@ -234,7 +234,7 @@ def main():
         if bands:
             dist.gather(fb, gathered, dst=0)
             if rank == 0:   # de-interleave: row r*world + g  <-  band g row r
-                frame.view(max_rows, world, width, 4).copy_(torch.stack(gathered, dim=1))
+                frame_box[0] = partition.deinterleave(gathered, height)
 
     def barrier():
         if world > 1:

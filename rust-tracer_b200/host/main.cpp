@@ -237,33 +237,53 @@ int main(int argc, char **argv) {
         Scene scene(level, gpus);  // Arc::new(Scene::default()), main.rs:23
         auto t1 = clk::now();
         double render_ms = 0.0, kernel_ms = 0.0;
-        for (unsigned f = 0; f < frames; f++) {
-            std::string path = output_file;
-            if (frames > 1 && output_file != "-") {
-                char suffix[32];
-                snprintf(suffix, sizeof(suffix), "%04u.tga", f);
-                path = with_extension(output_file, suffix);
-            }
-            if (output_file != "-") {
-                fp = fopen(path.c_str(), "wb");  // fs::File::create(&p).unwrap()
-                if (!fp) {
-                    fprintf(stderr, "thread 'main' panicked at 'called `Result::unwrap()` on an `Err` value: %s'\n", strerror(errno));
-                    return 101;
-                }
-                output = FileOrAnyWriter::file_writer(fp);
-            } else {
-                output = FileOrAnyWriter::any_writer_stdout();
-            }
-            rt_camera cam = orbit_camera(f, frames);
+        auto frame_path = [&](unsigned f) {
+            if (frames == 1 || output_file == "-") return output_file;
+            char suffix[32];
+            snprintf(suffix, sizeof(suffix), "%04u.tga", f);
+            return with_extension(output_file, suffix);
+        };
+        auto open_output = [&](unsigned f) {
+            if (output_file == "-") return FileOrAnyWriter::any_writer_stdout();
+            fp = fopen(frame_path(f).c_str(), "wb");  // fs::File::create(&p).unwrap()
+            if (!fp) throw Panic(std::string("called `Result::unwrap()` on an `Err` value: ") + strerror(errno));
+            return FileOrAnyWriter::file_writer(fp);
+        };
+        if (frames > 1 && gpus == 1) {
+            // orbit sweep on one GPU: copy-out of frame f overlaps the render of frame f+1
+            std::vector<rt_camera> cams;
+            for (unsigned f = 0; f < frames; f++) cams.push_back(orbit_camera(f, frames));
+            ImageRegion full;
+            full.l = 0, full.r = options.width, full.b = 0, full.t = options.height;
+            RGBABuffer staging(full);
             rt_stats st;
-            {
-                PPMStdoutRGBABufferWriter writer(true, &output);
-                auto r0 = clk::now();
-                Renderer::render(options, scene, writer, frames > 1 ? &cam : nullptr, &st);
-                render_ms += std::chrono::duration<double, std::milli>(clk::now() - r0).count();
-                kernel_ms += st.kernel_ms;
-            }  // final write on drop (render.rs:331-335)
-            if (fp) fclose(fp), fp = nullptr;
+            auto r0 = clk::now();
+            Renderer::render_sweep(options, scene, cams, [&](uint32_t f, const uint8_t *rgba, size_t len) {
+                output = open_output(f);
+                {
+                    PPMStdoutRGBABufferWriter writer(true, &output);
+                    writer.begin(options.width, options.height);
+                    staging.copy_from(rgba, len);
+                    writer.write_rgba_buffer(staging);
+                }
+                if (fp) fclose(fp), fp = nullptr;
+            }, &st);
+            render_ms += std::chrono::duration<double, std::milli>(clk::now() - r0).count();
+            kernel_ms = 0.0;
+        } else {
+            for (unsigned f = 0; f < frames; f++) {
+                output = open_output(f);
+                rt_camera cam = orbit_camera(f, frames);
+                rt_stats st;
+                {
+                    PPMStdoutRGBABufferWriter writer(true, &output);
+                    auto r0 = clk::now();
+                    Renderer::render(options, scene, writer, frames > 1 ? &cam : nullptr, &st);
+                    render_ms += std::chrono::duration<double, std::milli>(clk::now() - r0).count();
+                    kernel_ms += st.kernel_ms;
+                }  // final write on drop (render.rs:331-335)
+                if (fp) fclose(fp), fp = nullptr;
+            }
         }
         if (args.stats) {
             double scene_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();

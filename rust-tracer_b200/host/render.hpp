@@ -64,6 +64,8 @@ class RGBABuffer {
     static size_t components() { return 4; }
     uint8_t *data() { return buf_; }
     const uint8_t *buffer() const { return buf_; }
+    // Fill from a finished frame of the same region (the sweep hands out library-owned pinned memory).
+    void copy_from(const uint8_t *rgba, size_t len) { memcpy(buf_, rgba, len < len_ ? len : len_); }
     size_t len() const { return len_; }
     const ImageRegion &region() const { return reg_; }
 
@@ -208,6 +210,24 @@ struct Renderer {
                                        frame.data(), frame.len(), stats),
                  "Renderer::render");
         writer.write_rgba_buffer(frame);
+    }
+
+    // A sweep of frames on one GPU (extension): the device-to-host copy of frame f overlaps the
+    // render of frame f+1 (rt_render_sweep).  `sink(f, buffer)` is called once per frame, in order.
+    template <class Sink>
+    static void render_sweep(const RenderOptions &o, const Scene &scene, const std::vector<rt_camera> &cameras,
+                             Sink &&sink, rt_stats *stats = nullptr) {
+        struct Ctx {
+            Sink *sink;
+            const RenderOptions *o;
+        } ctx{&sink, &o};
+        auto trampoline = [](void *user, uint32_t frame, const uint8_t *rgba, size_t len) {
+            Ctx *c = static_cast<Ctx *>(user);
+            (*c->sink)(frame, rgba, len);
+        };
+        rt_check(rt_render_sweep(scene.replicas()[0], cameras.data(), (uint32_t)cameras.size(), o.width, o.height,
+                                 o.samples_per_pixel, trampoline, &ctx, stats),
+                 "Renderer::render_sweep");
     }
 };
 

@@ -1,0 +1,105 @@
+"""Command-line conformance of target/release/rtrace with the reference binary (src/rust/main.rs).
+
+The argument / environment / exit-code behaviour needs no GPU; the rendering runs are GPU tests and
+compare the written file with the reference's golden `make image` output."""
+import hashlib
+import json
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "target", "release", "rtrace")
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "rtrace_output_1024x768.json")))
+
+
+@pytest.fixture(scope="module")
+def rtrace():
+    if not os.path.exists(BIN):
+        subprocess.check_call(["make", "-s", "-C", ROOT, "rtrace"])
+    return BIN
+
+
+def run(rtrace, *args, env=None, cwd=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([rtrace] + list(args), capture_output=True, env=e, cwd=cwd, timeout=120)
+
+
+def test_missing_output_is_a_usage_error(rtrace):
+    r = run(rtrace)
+    assert r.returncode == 1 and b"<output>" in r.stderr and r.stdout == b""
+
+
+def test_bad_extension_prints_hint_on_stdout_and_exits_zero(rtrace, tmp_path):
+    # main.rs:66-71
+    r = run(rtrace, "picture.png", cwd=str(tmp_path))
+    assert r.returncode == 0
+    assert r.stdout == b"Output file 'picture.png' must have the tga extension, e.g. picture.tga\n"
+    assert not (tmp_path / "picture.png").exists()
+    r = run(rtrace, "noext", cwd=str(tmp_path))
+    assert r.returncode == 0 and b"noext.tga" in r.stdout
+
+
+def test_unparsable_numbers_panic_with_101(rtrace, tmp_path):
+    # main.rs:56,79-81: `.parse().unwrap()`
+    for flag in ("--width=abc", "--height=-3", "--samples-per-pixel=1.5", "--width=70000", "--num-cores=x"):
+        r = run(rtrace, flag, "o.tga", cwd=str(tmp_path))
+        assert r.returncode == 101, flag
+        assert b"panicked" in r.stderr
+
+
+def test_unknown_flag_and_extra_positional_are_usage_errors(rtrace, tmp_path):
+    assert run(rtrace, "--bogus", "o.tga", cwd=str(tmp_path)).returncode == 1
+    assert run(rtrace, "a.tga", "b.tga", cwd=str(tmp_path)).returncode == 1
+    assert run(rtrace, "--width", cwd=str(tmp_path)).returncode == 1
+    assert run(rtrace, "", cwd=str(tmp_path)).returncode == 1   # empty_values(false), main.rs:53
+
+
+def test_help_and_version(rtrace):
+    r = run(rtrace, "--help")
+    assert r.returncode == 0 and b"--samples-per-pixel" in r.stdout and b"--num-cores" in r.stdout
+    r = run(rtrace, "--version")
+    assert r.returncode == 0 and r.stdout.strip() == b"rtrace 0.2.0"   # main.rs:33
+
+
+def test_makefile_keeps_the_reference_targets():
+    mk = open(os.path.join(ROOT, "Makefile")).read()
+    for target in ("all: rtrace", "image: rtrace"):
+        assert target in mk
+    # the exact command line of the reference `make image` (Makefile:7)
+    assert "time ./target/release/rtrace --samples-per-pixel=4 --width=1024 --height=768 out.tga" in mk
+
+
+@pytest.mark.gpu
+def test_make_image_file_equals_reference_golden(rtrace, tmp_path):
+    """`make image`: out.tga is a binary PPM whose bytes equal the reference's shipped image."""
+    r = run(rtrace, "--samples-per-pixel=4", "--width=1024", "--height=768", "out.tga", cwd=str(tmp_path),
+            env={"RTRACEMAXPROCS": "4"})
+    assert r.returncode == 0, r.stderr
+    data = (tmp_path / "out.tga").read_bytes()
+    assert data.startswith(b"P6\n1024 768\n255\n") and len(data) == 15 + 1024 * 768 * 3
+    assert hashlib.sha256(data).hexdigest() == GOLD["ppm_sha256"]
+
+
+@pytest.mark.gpu
+def test_stdout_sink_and_flag_forms(rtrace, tmp_path):
+    a = run(rtrace, "--width", "64", "--height=128", "--samples-per-pixel", "2", "-")
+    assert a.returncode == 0 and a.stdout.startswith(b"P6\n64 128\n255\n") and len(a.stdout) == 14 + 64 * 128 * 3
+    b = run(rtrace, "--width=64", "--height=128", "--samples-per-pixel=2", "--num-cores=3", "x.tga", cwd=str(tmp_path))
+    assert b.returncode == 0 and (tmp_path / "x.tga").read_bytes() == a.stdout
+
+
+@pytest.mark.gpu
+def test_sizes_the_reference_rejects_and_extensions(rtrace, tmp_path):
+    # 100x60 is not a multiple of 64: the reference asserts (render.rs:265-266); here it renders
+    r = run(rtrace, "--width=100", "--height=60", "--level=5", "--stats", "e.tga", cwd=str(tmp_path))
+    assert r.returncode == 0 and b"rtrace-b200:" in r.stderr
+    assert (tmp_path / "e.tga").read_bytes().startswith(b"P6\n100 60\n255\n")
+    # orbit sweep: one file per frame, frame 0 is the reference camera
+    r = run(rtrace, "--width=64", "--height=64", "--frames=3", "s.tga", cwd=str(tmp_path))
+    assert r.returncode == 0
+    frames = [(tmp_path / ("s.%04d.tga" % f)).read_bytes() for f in range(3)]
+    one = run(rtrace, "--width=64", "--height=64", "-")
+    assert frames[0] == one.stdout and frames[1] != frames[0]
