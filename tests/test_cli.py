@@ -79,14 +79,16 @@ def test_make_image_file_equals_reference_golden(rtrace, tmp_path):
             env={"RTRACEMAXPROCS": "4"})
     assert r.returncode == 0, r.stderr
     data = (tmp_path / "out.tga").read_bytes()
-    assert data.startswith(b"P6\n1024 768\n255\n") and len(data) == 15 + 1024 * 768 * 3
+    hdr = b"P6\n1024 768\n255\n"
+    assert data.startswith(hdr) and len(data) == len(hdr) + 1024 * 768 * 3 == 2359312
     assert hashlib.sha256(data).hexdigest() == GOLD["ppm_sha256"]
 
 
 @pytest.mark.gpu
 def test_stdout_sink_and_flag_forms(rtrace, tmp_path):
     a = run(rtrace, "--width", "64", "--height=128", "--samples-per-pixel", "2", "-")
-    assert a.returncode == 0 and a.stdout.startswith(b"P6\n64 128\n255\n") and len(a.stdout) == 14 + 64 * 128 * 3
+    hdr = b"P6\n64 128\n255\n"
+    assert a.returncode == 0 and a.stdout.startswith(hdr) and len(a.stdout) == len(hdr) + 64 * 128 * 3
     b = run(rtrace, "--width=64", "--height=128", "--samples-per-pixel=2", "--num-cores=3", "x.tga", cwd=str(tmp_path))
     assert b.returncode == 0 and (tmp_path / "x.tga").read_bytes() == a.stdout
 
