@@ -174,14 +174,16 @@ int rt_trace_rays(const rt_scene *s, size_t n, const rt_ray *rays, rt_hit *hits)
  * a register-resident FMA chain on every SM (the roofline denominator). */
 int rt_measure_fp32_peak(int device, double *tflops, double *sm_clock_mhz);
 /* Diagnostics: mode 0 = FFMA chains, mode 1 = alternating FMUL/FADD chains (the
- * unfused mix the parity rule forces on the discriminant); TFLOP/s counted as 2
- * flop per FFMA and 1 per FMUL/FADD. */
+ * unfused mix the parity rule forces on the discriminant), mode 2 = packed FFMA2
+ * (sm_100 f32x2), mode 3 = packed FMUL2/FADD2; TFLOP/s counted as 2 flop per FMA
+ * and 1 per multiply or add, per component. */
 int rt_microbench_fp32(int device, int mode, double *tflops);
 
 /* Diagnostics: compares the kernels' branch-free Newton-step sqrt / reciprocal with
- * the IEEE-rounded intrinsics on n pseudo-random inputs; mismatches[0] = sqrt,
- * mismatches[1] = reciprocal (both must be 0). */
-int rt_selftest_math(uint32_t n, uint32_t seed, uint64_t mismatches[2]);
+ * the IEEE-rounded intrinsics, and the packed f32x2 versions of sqrt, reciprocal,
+ * ray-sphere distance and normalisation with the scalar ones, on n pseudo-random
+ * inputs; all six mismatch counters must be 0. */
+int rt_selftest_math(uint32_t n, uint32_t seed, uint64_t mismatches[6]);
 
 /* Pinned host memory for output buffers (what the CLI hands to rt_render_frame so
  * the device-to-host copy runs at full PCIe rate).  Replaces the Vec<u8> of

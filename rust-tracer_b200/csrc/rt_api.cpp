@@ -142,6 +142,7 @@ void fill_params(const rt_scene *s, const rt_camera *cam, uint32_t w, uint32_t h
     p.sph = s->d_sph;
     p.skip = s->d_skip;
     p.n_nodes = s->n;
+    p.one = 1.0f;
     p.level = s->flat.level;
     p.leaf_rmin = s->flat.leaf_rmin;
     for (int k = 0; k < 3; k++) p.scene_center[k] = s->flat.sph.empty() ? 0.0f : s->flat.sph[k];
@@ -785,19 +786,18 @@ int rt_microbench_fp32(int device, int mode, double *tflops) {
     return RT_OK;
 }
 
-int rt_selftest_math(uint32_t n, uint32_t seed, uint64_t mismatches[2]) {
+int rt_selftest_math(uint32_t n, uint32_t seed, uint64_t mismatches[6]) {
     if (!mismatches) return fail(RT_ERR_INVALID, "NULL argument");
     if (rt_device_count() == 0) return fail(RT_ERR_CUDA, "no CUDA device");
     unsigned long long *d = nullptr;
-    CUDA_TRY(cudaMalloc(&d, 16));
-    cudaError_t e = cudaMemset(d, 0, 16);
+    CUDA_TRY(cudaMalloc(&d, 48));
+    cudaError_t e = cudaMemset(d, 0, 48);
     if (e == cudaSuccess) e = rt_launch_math_selftest(n, seed, d, nullptr);
-    unsigned long long h[2] = {0, 0};
-    if (e == cudaSuccess) e = cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    unsigned long long h[6] = {0, 0, 0, 0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpy(h, d, 48, cudaMemcpyDeviceToHost);
     cudaFree(d);
     if (e != cudaSuccess) return fail(RT_ERR_CUDA, "math selftest: %s", cudaGetErrorString(e));
-    mismatches[0] = h[0];
-    mismatches[1] = h[1];
+    for (int k = 0; k < 6; k++) mismatches[k] = h[k];
     return RT_OK;
 }
 

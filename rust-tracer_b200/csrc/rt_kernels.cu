@@ -192,26 +192,47 @@ __global__ void trace_rays_kernel(const float4 *__restrict__ sph, const uint32_t
 }
 
 // Register-resident FP32 chains: the live roofline denominator.
-// mode 0: FFMA; mode 1: alternating FMUL / FADD (the unfused mix the parity rule forces).
+// mode 0: FFMA; mode 1: alternating FMUL / FADD (the unfused mix the parity rule forces);
+// mode 2: packed FFMA2 (sm_100 f32x2); mode 3: packed FMUL2 / FADD2.
 template <int MODE>
 __global__ void __launch_bounds__(256) fp32_peak_kernel(float *out, int iters, float a, float b) {
-    float r[16];
+    float s = 0.0f;
+    if (MODE < 2) {
+        float r[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) r[k] = (float)(threadIdx.x + k) * 1e-3f;
-    for (int it = 0; it < iters; it++) {
+        for (int k = 0; k < 16; k++) r[k] = (float)(threadIdx.x + k) * 1e-3f;
+        for (int it = 0; it < iters; it++) {
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            if (MODE == 0) {
-                r[k] = __fmaf_rn(r[k], a, b);
-            } else {
-                r[k] = __fmul_rn(r[k], a);
-                r[k] = __fadd_rn(r[k], b);
+            for (int k = 0; k < 16; k++) {
+                if (MODE == 0) {
+                    r[k] = __fmaf_rn(r[k], a, b);
+                } else {
+                    r[k] = __fmul_rn(r[k], a);
+                    r[k] = __fadd_rn(r[k], b);
+                }
             }
         }
-    }
-    float s = 0.0f;
 #pragma unroll
-    for (int k = 0; k < 16; k++) s += r[k];
+        for (int k = 0; k < 16; k++) s += r[k];
+    } else {
+        float2 r[8];
+        const float2 a2 = make_float2(a, a), b2 = make_float2(b, b);
+#pragma unroll
+        for (int k = 0; k < 8; k++) r[k] = make_float2((float)(threadIdx.x + k) * 1e-3f, (float)(threadIdx.x + k) * 2e-3f);
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (MODE == 2) {
+                    r[k] = __ffma2_rn(r[k], a2, b2);
+                } else {
+                    r[k] = __fmul2_rn(r[k], a2);
+                    r[k] = __fadd2_rn(r[k], b2);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) s += r[k].x + r[k].y;
+    }
     if (s == 12345.678f) out[0] = s;  // keep the chains alive
 }
 
@@ -252,7 +273,11 @@ cudaError_t rt_launch_trace_rays(const float4 *sph, const uint32_t *skip, uint32
 cudaError_t rt_launch_fp32_peak(int mode, float *out, int blocks, int iters, cudaStream_t stream) {
     if (mode == 0)
         fp32_peak_kernel<0><<<blocks, 256, 0, stream>>>(out, iters, 1.0000001f, 1e-7f);
-    else
+    else if (mode == 1)
         fp32_peak_kernel<1><<<blocks, 256, 0, stream>>>(out, iters, 1.0000001f, 1e-7f);
+    else if (mode == 2)
+        fp32_peak_kernel<2><<<blocks, 256, 0, stream>>>(out, iters, 1.0000001f, 1e-7f);
+    else
+        fp32_peak_kernel<3><<<blocks, 256, 0, stream>>>(out, iters, 1.0000001f, 1e-7f);
     return cudaGetLastError();
 }

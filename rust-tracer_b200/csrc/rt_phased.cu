@@ -23,7 +23,7 @@
 // A cull tile whose candidates do not fit the pool is flagged and its pixel tiles
 // fall back to the per-lane walk (lane_traverse): the output never depends on the
 // pool size.  Exactness argument: see rt_tile.cu.
-#include "rt_cull.cuh"
+#include "rt_pack.cuh"
 #include "rt_kernels.h"
 
 namespace rt {
@@ -31,6 +31,9 @@ namespace rt {
 static constexpr uint32_t NO_CHUNK = 0xffffffffu;
 static constexpr uint32_t OVERFLOWED = 0xfffffffeu;
 static constexpr int P_WARPS = 4;  // warps per block in every phase (independent warps)
+#ifndef RT_PHASED_MINBLOCKS
+#define RT_PHASED_MINBLOCKS 1
+#endif
 
 struct CullShared {
     float4 cand4[T_CAND];
@@ -66,8 +69,11 @@ RT_DEV PrimaryBeam cull_tile_beam(const RenderParams &p, uint32_t ct_x, uint32_t
     return make_primary_beam(p, (float)x0, (float)xh + frac, fminf(ya, yb), fmaxf(ya, yb) + frac);
 }
 
-// Append the warp's candidate list (n records of UNITS 16-byte units) to the pool
-// as a chunk {count, next} + records, chained in front of `head`.
+// Append the warp's candidate list to the pool as a chunk {count, next} + records, chained in
+// front of `head`.  Records are stored as broadcast PAIRS so that the packed f32x2 tests of K2 /
+// K4 (two rays per instruction) load their operands straight into register pairs:
+//   primary (3 units): {vx,vx,vy,vy} {vz,vz,-v.v,-v.v} {r*r,r*r,index,0}
+//   shadow  (2 units): {cx,cx,cy,cy} {cz,cz,r*r,r*r}
 template <int UNITS>
 RT_DEV uint32_t flush_chunk(const RenderParams &p, const CullShared &sm, int lane, uint32_t n, uint32_t head) {
     if (n == 0 || head == OVERFLOWED) return head;
@@ -79,10 +85,17 @@ RT_DEV uint32_t flush_chunk(const RenderParams &p, const CullShared &sm, int lan
     if (lane == 0) p.pool[base] = make_uint4(n, head, 0u, 0u);
     for (uint32_t c = lane; c < n; c += 32) {
         const float4 a = sm.cand4[c];
-        p.pool[base + 1u + UNITS * c] = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w));
-        if (UNITS == 2) {
+        const uint32_t ax = __float_as_uint(a.x), ay = __float_as_uint(a.y), az = __float_as_uint(a.z);
+        uint4 *rec = p.pool + base + 1u + UNITS * c;
+        rec[0] = make_uint4(ax, ax, ay, ay);
+        if (UNITS == 3) {
             const float2 e = sm.cand2[c];
-            p.pool[base + 2u + UNITS * c] = make_uint4(__float_as_uint(e.x), __float_as_uint(e.y), 0u, 0u);
+            const uint32_t nvv = __float_as_uint(-a.w), rr = __float_as_uint(e.x);
+            rec[1] = make_uint4(az, az, nvv, nvv);
+            rec[2] = make_uint4(rr, rr, __float_as_uint(e.y), 0u);
+        } else {
+            const uint32_t rr = __float_as_uint(a.w);
+            rec[1] = make_uint4(az, az, rr, rr);
         }
     }
     return base;
@@ -107,7 +120,7 @@ __global__ void __launch_bounds__(32 * P_WARPS) phase_cull_primary(const RenderP
     bool done;
     do {
         done = cull_run<true>(p, sm, pb, lane, cs);
-        head = flush_chunk<2>(p, sm, lane, cs.ncand, head);
+        head = flush_chunk<3>(p, sm, lane, cs.ncand, head);
         __syncwarp();
     } while (!done && head != OVERFLOWED);
     if (lane == 0) p.tile_hdr[ct] = make_uint4(head, NO_CHUNK, 0x7f800000u, 0u);
@@ -117,10 +130,9 @@ __global__ void __launch_bounds__(32 * P_WARPS) phase_cull_primary(const RenderP
 // K2: exact closest-hit tests, one warp per pixel tile
 // ---------------------------------------------------------------------------
 template <int SPP, int PXW, int PXH, int CW, int CH>
-__global__ void __launch_bounds__(32 * P_WARPS) phase_test_primary(const RenderParams p) {
+__global__ void __launch_bounds__(32 * P_WARPS, RT_PHASED_MINBLOCKS) phase_test_primary(const RenderParams p) {
     using G = Geo<SPP, PXW, PXH, CW, CH>;
     constexpr int S = G::S, NS = G::NS;
-    constexpr int GS = 2;  // slots processed together
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const G geo(p.width, p.row_count);
     const uint32_t pt = blockIdx.x * P_WARPS + warp;
@@ -129,6 +141,7 @@ __global__ void __launch_bounds__(32 * P_WARPS) phase_test_primary(const RenderP
     const uint32_t ct = (pt_y / CH) * geo.ctiles_x + pt_x / CW;
     const uint32_t tile_x0 = pt_x * G::TW, tile_j0 = pt_y * G::TH;
     const V3 eye = v3(p.eye[0], p.eye[1], p.eye[2]);
+    const ONE2 one = f2s(p.one);  // 1.0f the compiler cannot see (rt_pack.cuh)
     uint32_t *winner = p.winner + (size_t)pt * S * 32;
 
     uint32_t bx, bj;  // first pixel of this lane's block
@@ -172,41 +185,35 @@ __global__ void __launch_bounds__(32 * P_WARPS) phase_test_primary(const RenderP
         // candidates c0..c1 (at most 32) of a chunk -> bit mask of those this LANE's block can see.
         // First every lane tests ONE candidate against the warp tile's cone (ballot), then each lane
         // tests the survivors against its own cone.
+        auto cand_test = [&](const PrimaryBeam &beam, uint32_t base, uint32_t c) {
+            const uint4 u0 = __ldg(&p.pool[base + 1u + 3u * c]);
+            const uint4 u1 = __ldg(&p.pool[base + 2u + 3u * c]);
+            const uint4 u2 = __ldg(&p.pool[base + 3u + 3u * c]);
+            const float4 af = make_float4(__uint_as_float(u0.x), __uint_as_float(u0.z), __uint_as_float(u1.x), -__uint_as_float(u1.z));
+            return lane_test(beam, af, __uint_as_float(u2.x));
+        };
         auto chunk_mask = [&](uint32_t base, uint32_t c0, uint32_t c1) {
-            bool w_ok = false;
-            if (c0 + lane < c1) {
-                const uint4 a = __ldg(&p.pool[base + 1u + 2u * (c0 + lane)]);
-                const uint4 e = __ldg(&p.pool[base + 2u + 2u * (c0 + lane)]);
-                const float4 af = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w));
-                w_ok = lane_test(wb, af, __uint_as_float(e.x));
-            }
+            const bool w_ok = (c0 + lane < c1) && cand_test(wb, base, c0 + lane);
             uint32_t mask = 0;
             for (uint32_t wm = __ballot_sync(FULLMASK, w_ok); wm; wm &= wm - 1u) {
                 const uint32_t c = c0 + (uint32_t)__ffs((int)wm) - 1u;
-                const uint4 a = __ldg(&p.pool[base + 1u + 2u * c]);
-                const uint4 e = __ldg(&p.pool[base + 2u + 2u * c]);
-                const float4 af = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w));
-                if (lane_in && lane_test(lb, af, __uint_as_float(e.x))) mask |= 1u << (c - c0);
+                if (lane_in && cand_test(lb, base, c)) mask |= 1u << (c - c0);
             }
             return mask;
         };
-        // mask of the first 32 candidates of the first chunk: reused by every slot group
+        // mask of the first 32 candidates of the first chunk: reused by every slot pair
         uint32_t mask0 = 0;
         if (head != NO_CHUNK) mask0 = chunk_mask(head, 0u, min(__ldg(&p.pool[head]).x, 32u));
 #pragma unroll 1
-        for (int s0 = 0; s0 < S; s0 += GS) {
-            V3 d[GS];
-            float bd[GS];
-            uint32_t bi[GS];
-#pragma unroll
-            for (int k = 0; k < GS; k++) {
-                const int s = (s0 + k < S) ? s0 + k : S - 1;
-                uint32_t x, j;
-                slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s / NS, x, j);
-                d[k] = slot_dir<SPP>(p, x, p.row_start + j * p.row_stride, s % NS);
-                bd[k] = RT_INF;
-                bi[k] = NO_HIT;
-            }
+        for (int s0 = 0; s0 < S; s0 += 2) {  // two slots per pass: packed f32x2 arithmetic
+            const int s1 = (s0 + 1 < S) ? s0 + 1 : s0;
+            uint32_t x0, j0, x1, j1;
+            slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s0 / NS, x0, j0);
+            slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s1 / NS, x1, j1);
+            const V3x2 d = slot_dir2<SPP>(one, p, x0, p.row_start + j0 * p.row_stride, s0 % NS, x1,
+                                          p.row_start + j1 * p.row_stride, s1 % NS);
+            F2 bd = f2s(RT_INF);
+            uint32_t bi0 = NO_HIT, bi1 = NO_HIT;
             for (uint32_t base = head; base != NO_CHUNK;) {
                 const uint4 hdr = __ldg(&p.pool[base]);
                 const uint32_t n = hdr.x;
@@ -214,32 +221,29 @@ __global__ void __launch_bounds__(32 * P_WARPS) phase_test_primary(const RenderP
                     const uint32_t mask = (base == head && c0 == 0) ? mask0 : chunk_mask(base, c0, min(n, c0 + 32u));
                     for (uint32_t m = mask; m; m &= m - 1u) {
                         const uint32_t c = c0 + (uint32_t)__ffs((int)m) - 1u;
-                        const uint4 a = __ldg(&p.pool[base + 1u + 2u * c]);
-                        const uint4 e = __ldg(&p.pool[base + 2u + 2u * c]);
-                        const V3 v = v3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
-                        const uint32_t idx = e.y;
-#pragma unroll
-                        for (int k = 0; k < GS; k++) {
-                            const float dist = primary_distance(v, __uint_as_float(a.w), __uint_as_float(e.x), d[k]);
-                            // primitive.rs:79 + pre-order visiting: strictly closer wins, ties -> lowest index
-                            if (dist < bd[k] || (dist == bd[k] && idx < bi[k] && bi[k] != NO_HIT)) {
-                                bd[k] = dist;
-                                bi[k] = idx;
-                            }
-                        }
+                        const uint4 u0 = __ldg(&p.pool[base + 1u + 3u * c]);
+                        const uint4 u1 = __ldg(&p.pool[base + 2u + 3u * c]);
+                        const uint4 u2 = __ldg(&p.pool[base + 3u + 3u * c]);
+                        V3x2 v;
+                        v.x = f2(__uint_as_float(u0.x), __uint_as_float(u0.y));
+                        v.y = f2(__uint_as_float(u0.z), __uint_as_float(u0.w));
+                        v.z = f2(__uint_as_float(u1.x), __uint_as_float(u1.y));
+                        const F2 nvv = f2(__uint_as_float(u1.z), __uint_as_float(u1.w));
+                        const F2 rr = f2(__uint_as_float(u2.x), __uint_as_float(u2.y));
+                        const uint32_t idx = u2.z;
+                        const F2 dist = primary_distance2(one, v, nvv, rr, d);
+                        // primitive.rs:79 + pre-order visiting: strictly closer wins, ties -> lowest index
+                        if (dist.x < bd.x || (dist.x == bd.x && idx < bi0 && bi0 != NO_HIT)) bd.x = dist.x, bi0 = idx;
+                        if (dist.y < bd.y || (dist.y == bd.y && idx < bi1 && bi1 != NO_HIT)) bd.y = dist.y, bi1 = idx;
                     }
                 }
                 base = hdr.y;
             }
-#pragma unroll
-            for (int k = 0; k < GS; k++) {
-                if (s0 + k < S) {
-                    winner[(s0 + k) * 32 + lane] = bi[k];
-                    if (bi[k] != NO_HIT) {
-                        tmin = fminf(tmin, fabsf(bd[k]));
-                        tmax = fmaxf(tmax, fabsf(bd[k]));
-                    }
-                }
+            winner[s0 * 32 + lane] = bi0;
+            if (bi0 != NO_HIT) tmin = fminf(tmin, fabsf(bd.x)), tmax = fmaxf(tmax, fabsf(bd.x));
+            if (s1 != s0) {
+                winner[s1 * 32 + lane] = bi1;
+                if (bi1 != NO_HIT) tmin = fminf(tmin, fabsf(bd.y)), tmax = fmaxf(tmax, fabsf(bd.y));
             }
         }
     }
@@ -306,7 +310,7 @@ __global__ void __launch_bounds__(32 * P_WARPS) phase_cull_shadow(const RenderPa
     bool done;
     do {
         done = cull_run<false>(p, sm, sb, lane, cs);
-        head = flush_chunk<1>(p, sm, lane, cs.ncand, head);
+        head = flush_chunk<2>(p, sm, lane, cs.ncand, head);
         __syncwarp();
     } while (!done && head != OVERFLOWED);
     if (lane == 0) reinterpret_cast<uint32_t *>(&p.tile_hdr[ct])[1] = head;
@@ -316,10 +320,9 @@ __global__ void __launch_bounds__(32 * P_WARPS) phase_cull_shadow(const RenderPa
 // K4: shading, shadow tests, accumulation, store; one warp per pixel tile
 // ---------------------------------------------------------------------------
 template <int SPP, int PXW, int PXH, int CW, int CH, bool DIAG>
-__global__ void __launch_bounds__(32 * P_WARPS) phase_shade_store(const RenderParams p) {
+__global__ void __launch_bounds__(32 * P_WARPS, RT_PHASED_MINBLOCKS) phase_shade_store(const RenderParams p) {
     using G = Geo<SPP, PXW, PXH, CW, CH>;
     constexpr int S = G::S, NS = G::NS;
-    constexpr int GS = 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const G geo(p.width, p.row_count);
     const uint32_t pt = blockIdx.x * P_WARPS + warp;
@@ -328,6 +331,7 @@ __global__ void __launch_bounds__(32 * P_WARPS) phase_shade_store(const RenderPa
     const uint32_t ct = (pt_y / CH) * geo.ctiles_x + pt_x / CW;
     const uint32_t tile_x0 = pt_x * G::TW, tile_j0 = pt_y * G::TH;
     const uint32_t *winner = p.winner + (size_t)pt * S * 32;
+    const ONE2 one = f2s(p.one);  // 1.0f the compiler cannot see (rt_pack.cuh)
 
     const V3 eye = v3(p.eye[0], p.eye[1], p.eye[2]);
     const V3 light = v3(p.light[0], p.light[1], p.light[2]);
@@ -365,37 +369,41 @@ __global__ void __launch_bounds__(32 * P_WARPS) phase_shade_store(const RenderPa
             }
         }
     } else if (lane_in) {
+        const V3x2 eye2 = v3x2s(eye), light2 = v3x2s(light), to_light2 = v3x2s(to_light);
 #pragma unroll 1
-        for (int s0 = 0; s0 < S; s0 += GS) {
-            V3 o[GS];
-            float g[GS];
-            uint32_t pend = 0;  // bit k: slot s0+k casts a shadow ray that is still unoccluded
-            uint32_t occluded = 0;
-#pragma unroll
-            for (int k = 0; k < GS; k++) {
-                const int s = (s0 + k < S) ? s0 + k : S - 1;
-                uint32_t x, j;
-                slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s / NS, x, j);
-                const V3 d = slot_dir<SPP>(p, x, p.row_start + j * p.row_stride, s % NS);
-                const uint32_t wi = winner[s * 32 + lane];
-                const bool hit = wi != NO_HIT;
-                const float4 w = __ldg(&p.sph[hit ? wi : 0u]);
-                const V3 v = vsub(v3(w.x, w.y, w.z), eye);
-                const float dist = hit ? primary_distance(v, vdot(v, v), fmul(w.w, w.w), d) : 1.0f;
-                // primitive.rs:83 normal; render.rs:194 g; render.rs:199 shadow origin
-                const V3 nrm = vnormalized_nr(vadd(eye, vsub(vmulf(d, dist), v3(w.x, w.y, w.z))));
-                const float gg = vdot(nrm, light);
-                o[k] = vadd(vadd(eye, vmulf(d, dist)), vmulf(nrm, fmul(dist, sqrt_eps)));
-                g[k] = hit ? gg : RT_INF;
-                if (hit && !(gg >= 0.0f) && s0 + k < S) pend |= 1u << k;
-            }
+        for (int s0 = 0; s0 < S; s0 += 2) {  // two slots per pass: packed f32x2 arithmetic
+            const int s1 = (s0 + 1 < S) ? s0 + 1 : s0;
+            uint32_t x0, j0, x1, j1;
+            slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s0 / NS, x0, j0);
+            slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s1 / NS, x1, j1);
+            const V3x2 d = slot_dir2<SPP>(one, p, x0, p.row_start + j0 * p.row_stride, s0 % NS, x1,
+                                          p.row_start + j1 * p.row_stride, s1 % NS);
+            const uint32_t wi0 = winner[s0 * 32 + lane], wi1 = winner[s1 * 32 + lane];
+            const bool hit0 = wi0 != NO_HIT, hit1 = wi1 != NO_HIT;
+            const float4 w0 = __ldg(&p.sph[hit0 ? wi0 : 0u]), w1 = __ldg(&p.sph[hit1 ? wi1 : 0u]);
+            const V3x2 cen = V3x2{f2(w0.x, w1.x), f2(w0.y, w1.y), f2(w0.z, w1.z)};
+            const F2 rad = f2(w0.w, w1.w);
+            // the winner's distance again (primitive.rs:55-72), exactly as K2 computed it
+            const V3x2 v = vsub2(one, cen, eye2);
+            F2 dist = primary_distance2(one, v, f2neg(vdot2(one, v, v)), f2mul(rad, rad), d);
+            if (!hit0) dist.x = 1.0f;
+            if (!hit1) dist.y = 1.0f;
+            // primitive.rs:83 normal; render.rs:194 g; render.rs:199 shadow origin
+            const V3x2 nrm = vnormalized2(one, vadd2(one, eye2, vsub2(one, vmulf2(d, dist), cen)));
+            const F2 gg = vdot2(one, nrm, light2);
+            const V3x2 o = vadd2(one, vadd2(one, eye2, vmulf2(d, dist)), vmulf2(nrm, f2mul(dist, f2s(sqrt_eps))));
+            const V3x2 no = V3x2{f2neg(o.x), f2neg(o.y), f2neg(o.z)};
+            float g[2] = {hit0 ? gg.x : RT_INF, hit1 ? gg.y : RT_INF};
+            uint32_t pend = 0, occluded = 0;  // bit k: slot k still needs / has found an occluder
+            if (hit0 && !(gg.x >= 0.0f)) pend |= 1u;
+            if (hit1 && !(gg.y >= 0.0f) && s1 != s0) pend |= 2u;
             if (head == OVERFLOWED) {  // per-lane walk, any-hit (render.rs:202-208)
 #pragma unroll
-                for (int k = 0; k < GS; k++) {
+                for (int k = 0; k < 2; k++) {
                     if ((pend >> k) & 1u) {
                         float sh = RT_INF;
                         uint32_t dummy = 0;
-                        lane_traverse<true>(p.sph, p.skip, p.n_nodes, o[k], to_light, sh, dummy);
+                        lane_traverse<true>(p.sph, p.skip, p.n_nodes, k ? hi(o) : lo(o), to_light, sh, dummy);
                         if (sh != RT_INF) occluded |= 1u << k;
                     }
                 }
@@ -404,33 +412,37 @@ __global__ void __launch_bounds__(32 * P_WARPS) phase_shade_store(const RenderPa
             for (uint32_t base = head; base < OVERFLOWED && pend;) {
                 const uint4 hdr = __ldg(&p.pool[base]);
                 for (uint32_t ci = 0; ci < hdr.x && pend; ci++) {
-                    const uint4 au = __ldg(&p.pool[base + 1u + ci]);
-                    const V3 cc = v3(__uint_as_float(au.x), __uint_as_float(au.y), __uint_as_float(au.z));
-#pragma unroll
-                    for (int k = 0; k < GS; k++) {
-                        // primitive.rs:56-58 for the shadow ray {pos: o, dir: -light}
-                        const V3 v = vsub(cc, o[k]);
-                        const float b = vdot(v, to_light);
-                        const float disc = fadd(fsub(fmul(b, b), vdot(v, v)), __uint_as_float(au.w));
-                        // finite iff disc >= 0 and !(b + sqrt(disc) < 0) (primitive.rs:60-68); b >= 0 settles the latter
-                        bool f = !(disc < 0.0f);
-                        if (f && b < 0.0f) f = !(fadd(b, fsqrt_nr(disc)) < 0.0f);
-                        if (f && ((pend >> k) & 1u)) {
-                            pend &= ~(1u << k);
-                            occluded |= 1u << k;
-                        }
+                    const uint4 u0 = __ldg(&p.pool[base + 1u + 2u * ci]);
+                    const uint4 u1 = __ldg(&p.pool[base + 2u + 2u * ci]);
+                    V3x2 cc;
+                    cc.x = f2(__uint_as_float(u0.x), __uint_as_float(u0.y));
+                    cc.y = f2(__uint_as_float(u0.z), __uint_as_float(u0.w));
+                    cc.z = f2(__uint_as_float(u1.x), __uint_as_float(u1.y));
+                    const F2 rr = f2(__uint_as_float(u1.z), __uint_as_float(u1.w));
+                    // primitive.rs:56-58 for the shadow rays {pos: o, dir: -light}
+                    const V3x2 sv = vadd2(one, cc, no);  // center - ray.pos
+                    const F2 b = vdot2(one, sv, to_light2);
+                    const F2 disc = f2add(one, f2sub(one, f2mul(b, b), vdot2(one, sv, sv)), rr);
+                    // finite iff disc >= 0 and !(b + sqrt(disc) < 0) (primitive.rs:60-68); b >= 0 settles the latter
+                    bool f0 = !(disc.x < 0.0f), f1 = !(disc.y < 0.0f);
+                    if ((f0 && b.x < 0.0f) || (f1 && b.y < 0.0f)) {
+                        const F2 t2 = f2add(one, b, fsqrt_nr2(disc));
+                        f0 = f0 && !(t2.x < 0.0f);
+                        f1 = f1 && !(t2.y < 0.0f);
                     }
+                    const uint32_t f = ((f0 ? 1u : 0u) | (f1 ? 2u : 0u)) & pend;
+                    pend &= ~f;
+                    occluded |= f;
                 }
                 base = hdr.y;
             }
             // accumulate in reference sample order (render.rs:236-250), quantise, store (render.rs:92-109)
 #pragma unroll
-            for (int k = 0; k < GS; k++) {
+            for (int k = 0; k < 2; k++) {
                 const int s = s0 + k;
                 if (s < S) {
                     const int pi = s / NS, smp = s % NS;
-                    uint32_t x, j;
-                    slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, pi, x, j);
+                    const uint32_t x = k ? x1 : x0, j = k ? j1 : j0;
                     const bool inside = x < p.width && j < p.row_count;
                     if (smp == 0) {
                         c = v3(0.0f, 0.0f, 0.0f);
@@ -456,6 +468,7 @@ __global__ void __launch_bounds__(32 * P_WARPS) phase_shade_store(const RenderPa
                             kind = K_SHADOWED;
                         }
                     }
+                    (void)pi;
                     if (DIAG && p.kinds && inside) p.kinds[((size_t)j * p.width + x) * NS + smp] = kind;
                     if (smp == NS - 1 && inside) {
                         const V3 q = vmulf(c, recip);
@@ -529,7 +542,7 @@ void rt_phased_scratch(uint32_t width, uint32_t rows, uint32_t spp, int shape, s
 #undef RT_GEO
     *winner_bytes = (size_t)np * S * 32 * sizeof(uint32_t);
     *hdr_bytes = (size_t)nc * sizeof(uint4);
-    uint64_t units = (uint64_t)nc * 256u;
+    uint64_t units = (uint64_t)nc * 384u;
     if (units < (1u << 20)) units = 1u << 20;
     if (units > (1u << 26)) units = 1u << 26;  // 1 GiB of 16-byte units
     *pool_units = (uint32_t)units;

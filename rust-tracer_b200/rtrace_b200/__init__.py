@@ -334,9 +334,9 @@ def microbench_fp32(device, mode):
 
 
 def selftest_math(n=1 << 24, seed=1):
-    m = (C.c_uint64 * 2)()
+    m = (C.c_uint64 * 6)()
     _check(lib().rt_selftest_math(n, seed, m))
-    return int(m[0]), int(m[1])
+    return tuple(int(v) for v in m)
 
 
 class PinnedBuffer:
