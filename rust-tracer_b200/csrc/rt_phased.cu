@@ -130,15 +130,16 @@ __global__ void __launch_bounds__(32 * P_WARPS) phase_cull_primary(const RenderP
 // K2: exact closest-hit tests, one warp per pixel tile
 // ---------------------------------------------------------------------------
 template <int SPP, int PXW, int PXH, int CW, int CH>
-__global__ void __launch_bounds__(32 * P_WARPS, RT_PHASED_MINBLOCKS) phase_test_primary(const RenderParams p) {
+__global__ void __launch_bounds__(32 * CW * CH, RT_PHASED_MINBLOCKS) phase_test_primary(const RenderParams p) {
     using G = Geo<SPP, PXW, PXH, CW, CH>;
     constexpr int S = G::S, NS = G::NS;
+    __shared__ uint4 stage[1 + 3 * T_CAND];  // the cull tile's first candidate chunk, shared by its pixel tiles
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const G geo(p.width, p.row_count);
-    const uint32_t pt = blockIdx.x * P_WARPS + warp;
-    if (pt >= geo.n_ptiles()) return;
-    const uint32_t pt_x = pt % geo.ptiles_x, pt_y = pt / geo.ptiles_x;
-    const uint32_t ct = (pt_y / CH) * geo.ctiles_x + pt_x / CW;
+    // one block per cull tile, one warp per pixel tile of it
+    const uint32_t ct = blockIdx.x;
+    const uint32_t pt_x = (ct % geo.ctiles_x) * CW + (uint32_t)(warp % CW), pt_y = (ct / geo.ctiles_x) * CH + (uint32_t)(warp / CW);
+    const uint32_t pt = pt_y * geo.ptiles_x + pt_x;
     const uint32_t tile_x0 = pt_x * G::TW, tile_j0 = pt_y * G::TH;
     const V3 eye = v3(p.eye[0], p.eye[1], p.eye[2]);
     const ONE2 one = f2s(p.one);  // 1.0f the compiler cannot see (rt_pack.cuh)
@@ -149,6 +150,13 @@ __global__ void __launch_bounds__(32 * P_WARPS, RT_PHASED_MINBLOCKS) phase_test_
     const bool lane_in = bx < p.width && bj < p.row_count;
     const uint32_t head = p.tile_hdr[ct].x;
     if (head == NO_CHUNK) return;  // no candidate at all: K4 sees an empty hit range and never reads the winners
+    if (head != OVERFLOWED) {      // stage the first chunk (almost always the only one) in shared memory
+        const uint32_t units = 1u + 3u * __ldg(&p.pool[head]).x;
+        for (uint32_t u = threadIdx.x; u < units; u += blockDim.x) stage[u] = __ldg(&p.pool[head + u]);
+    }
+    __syncthreads();
+    if (pt_x >= geo.ptiles_x || pt_y >= geo.ptiles_y) return;  // cull tile on the frame edge
+    auto fetch = [&](uint32_t base, uint32_t off) { return base == head ? stage[off] : __ldg(&p.pool[base + off]); };
     float tmin = RT_INF, tmax = 0.0f;
 
     if (head == OVERFLOWED) {  // pool exhausted for this cull tile: the per-lane walk (group.rs:72-83)
@@ -186,9 +194,7 @@ __global__ void __launch_bounds__(32 * P_WARPS, RT_PHASED_MINBLOCKS) phase_test_
         // First every lane tests ONE candidate against the warp tile's cone (ballot), then each lane
         // tests the survivors against its own cone.
         auto cand_test = [&](const PrimaryBeam &beam, uint32_t base, uint32_t c) {
-            const uint4 u0 = __ldg(&p.pool[base + 1u + 3u * c]);
-            const uint4 u1 = __ldg(&p.pool[base + 2u + 3u * c]);
-            const uint4 u2 = __ldg(&p.pool[base + 3u + 3u * c]);
+            const uint4 u0 = fetch(base, 1u + 3u * c), u1 = fetch(base, 2u + 3u * c), u2 = fetch(base, 3u + 3u * c);
             const float4 af = make_float4(__uint_as_float(u0.x), __uint_as_float(u0.z), __uint_as_float(u1.x), -__uint_as_float(u1.z));
             return lane_test(beam, af, __uint_as_float(u2.x));
         };
@@ -203,7 +209,7 @@ __global__ void __launch_bounds__(32 * P_WARPS, RT_PHASED_MINBLOCKS) phase_test_
         };
         // mask of the first 32 candidates of the first chunk: reused by every slot pair
         uint32_t mask0 = 0;
-        if (head != NO_CHUNK) mask0 = chunk_mask(head, 0u, min(__ldg(&p.pool[head]).x, 32u));
+        if (head != NO_CHUNK) mask0 = chunk_mask(head, 0u, min(stage[0].x, 32u));
 #pragma unroll 1
         for (int s0 = 0; s0 < S; s0 += 2) {  // two slots per pass: packed f32x2 arithmetic
             const int s1 = (s0 + 1 < S) ? s0 + 1 : s0;
@@ -215,15 +221,13 @@ __global__ void __launch_bounds__(32 * P_WARPS, RT_PHASED_MINBLOCKS) phase_test_
             F2 bd = f2s(RT_INF);
             uint32_t bi0 = NO_HIT, bi1 = NO_HIT;
             for (uint32_t base = head; base != NO_CHUNK;) {
-                const uint4 hdr = __ldg(&p.pool[base]);
+                const uint4 hdr = fetch(base, 0u);
                 const uint32_t n = hdr.x;
                 for (uint32_t c0 = 0; c0 < n; c0 += 32) {
                     const uint32_t mask = (base == head && c0 == 0) ? mask0 : chunk_mask(base, c0, min(n, c0 + 32u));
                     for (uint32_t m = mask; m; m &= m - 1u) {
                         const uint32_t c = c0 + (uint32_t)__ffs((int)m) - 1u;
-                        const uint4 u0 = __ldg(&p.pool[base + 1u + 3u * c]);
-                        const uint4 u1 = __ldg(&p.pool[base + 2u + 3u * c]);
-                        const uint4 u2 = __ldg(&p.pool[base + 3u + 3u * c]);
+                        const uint4 u0 = fetch(base, 1u + 3u * c), u1 = fetch(base, 2u + 3u * c), u2 = fetch(base, 3u + 3u * c);
                         V3x2 v;
                         v.x = f2(__uint_as_float(u0.x), __uint_as_float(u0.y));
                         v.y = f2(__uint_as_float(u0.z), __uint_as_float(u0.w));
@@ -320,15 +324,16 @@ __global__ void __launch_bounds__(32 * P_WARPS) phase_cull_shadow(const RenderPa
 // K4: shading, shadow tests, accumulation, store; one warp per pixel tile
 // ---------------------------------------------------------------------------
 template <int SPP, int PXW, int PXH, int CW, int CH, bool DIAG>
-__global__ void __launch_bounds__(32 * P_WARPS, RT_PHASED_MINBLOCKS) phase_shade_store(const RenderParams p) {
+__global__ void __launch_bounds__(32 * CW * CH, RT_PHASED_MINBLOCKS) phase_shade_store(const RenderParams p) {
     using G = Geo<SPP, PXW, PXH, CW, CH>;
     constexpr int S = G::S, NS = G::NS;
+    __shared__ uint4 stage[1 + 2 * T_CAND];  // the cull tile's first shadow-candidate chunk
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const G geo(p.width, p.row_count);
-    const uint32_t pt = blockIdx.x * P_WARPS + warp;
-    if (pt >= geo.n_ptiles()) return;
-    const uint32_t pt_x = pt % geo.ptiles_x, pt_y = pt / geo.ptiles_x;
-    const uint32_t ct = (pt_y / CH) * geo.ctiles_x + pt_x / CW;
+    // one block per cull tile, one warp per pixel tile of it
+    const uint32_t ct = blockIdx.x;
+    const uint32_t pt_x = (ct % geo.ctiles_x) * CW + (uint32_t)(warp % CW), pt_y = (ct / geo.ctiles_x) * CH + (uint32_t)(warp / CW);
+    const uint32_t pt = pt_y * geo.ptiles_x + pt_x;
     const uint32_t tile_x0 = pt_x * G::TW, tile_j0 = pt_y * G::TH;
     const uint32_t *winner = p.winner + (size_t)pt * S * 32;
     const ONE2 one = f2s(p.one);  // 1.0f the compiler cannot see (rt_pack.cuh)
@@ -348,6 +353,13 @@ __global__ void __launch_bounds__(32 * P_WARPS, RT_PHASED_MINBLOCKS) phase_shade
     const bool lane_in = bx < p.width && bj < p.row_count;
     const uint4 tile_hdr = p.tile_hdr[ct];
     const uint32_t head = tile_hdr.y;
+    if (head < OVERFLOWED) {  // stage the first chunk (almost always the only one) in shared memory
+        const uint32_t units = 1u + 2u * __ldg(&p.pool[head]).x;
+        for (uint32_t u = threadIdx.x; u < units; u += blockDim.x) stage[u] = __ldg(&p.pool[head + u]);
+    }
+    __syncthreads();
+    if (pt_x >= geo.ptiles_x || pt_y >= geo.ptiles_y) return;  // cull tile on the frame edge
+    auto fetch = [&](uint32_t base, uint32_t off) { return base == head ? stage[off] : __ldg(&p.pool[base + off]); };
     unsigned n_hits = 0, n_shadow = 0;
     V3 c = v3(0.0f, 0.0f, 0.0f);  // colour / alpha of the pixel being accumulated (render.rs:233-234)
     float alpha = 0.0f;
@@ -410,10 +422,9 @@ __global__ void __launch_bounds__(32 * P_WARPS, RT_PHASED_MINBLOCKS) phase_shade
                 pend = 0;
             }
             for (uint32_t base = head; base < OVERFLOWED && pend;) {
-                const uint4 hdr = __ldg(&p.pool[base]);
+                const uint4 hdr = fetch(base, 0u);
                 for (uint32_t ci = 0; ci < hdr.x && pend; ci++) {
-                    const uint4 u0 = __ldg(&p.pool[base + 1u + 2u * ci]);
-                    const uint4 u1 = __ldg(&p.pool[base + 2u + 2u * ci]);
+                    const uint4 u0 = fetch(base, 1u + 2u * ci), u1 = fetch(base, 2u + 2u * ci);
                     V3x2 cc;
                     cc.x = f2(__uint_as_float(u0.x), __uint_as_float(u0.y));
                     cc.y = f2(__uint_as_float(u0.z), __uint_as_float(u0.w));
@@ -503,14 +514,14 @@ static cudaError_t launch_phased(bool diag, const RenderParams &p, cudaStream_t 
     if (nc == 0 || np == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(p.pool_count, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
-    const unsigned cb = (nc + P_WARPS - 1) / P_WARPS, pb = (np + P_WARPS - 1) / P_WARPS;
+    const unsigned cb = (nc + P_WARPS - 1) / P_WARPS;
     phase_cull_primary<SPP, PXW, PXH, CW, CH><<<cb, 32 * P_WARPS, 0, stream>>>(p);
-    phase_test_primary<SPP, PXW, PXH, CW, CH><<<pb, 32 * P_WARPS, 0, stream>>>(p);
+    phase_test_primary<SPP, PXW, PXH, CW, CH><<<nc, 32 * CW * CH, 0, stream>>>(p);
     phase_cull_shadow<SPP, PXW, PXH, CW, CH><<<cb, 32 * P_WARPS, 0, stream>>>(p);
     if (diag)
-        phase_shade_store<SPP, PXW, PXH, CW, CH, true><<<pb, 32 * P_WARPS, 0, stream>>>(p);
+        phase_shade_store<SPP, PXW, PXH, CW, CH, true><<<nc, 32 * CW * CH, 0, stream>>>(p);
     else
-        phase_shade_store<SPP, PXW, PXH, CW, CH, false><<<pb, 32 * P_WARPS, 0, stream>>>(p);
+        phase_shade_store<SPP, PXW, PXH, CW, CH, false><<<nc, 32 * CW * CH, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
