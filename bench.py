@@ -178,6 +178,9 @@ def main():
     ap.add_argument("--mode", default="frames", choices=["frames", "bands"],
                     help="N>1: 'frames' = each rank renders whole frames (weak); 'bands' = one frame split "
                          "into interleaved rows gathered to rank 0 over NCCL (strong)")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="bands mode: 'peer' = every rank's kernel stores its rows straight into rank 0's frame "
+                         "through CUDA-IPC peer memory over NVLink; 'nccl' = dist.gather of the bands + de-interleave")
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-l2-flush", action="store_true")
@@ -218,6 +221,18 @@ def main():
     fb = torch.zeros((max_rows, width, 4), dtype=torch.uint8, device="cuda")
     gathered = [torch.zeros_like(fb) for _ in range(world)] if (bands and rank == 0) else None
     frame_box = [None]
+    peer = bands and args.gather == "peer"
+    peer_ptr, peer_pitch = None, 0
+    if peer:
+        # rank 0 owns the frame; the others map it through a CUDA IPC handle and write their rows into it
+        handle = torch.zeros(64, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            frame_base = rt.device_alloc(height * width * 4)
+            handle.copy_(torch.frombuffer(bytearray(rt.ipc_export(frame_base)), dtype=torch.uint8))
+        dist.broadcast(handle, src=0)
+        if rank != 0:
+            frame_base = rt.ipc_open(bytes(handle.cpu().numpy().tobytes()))
+        peer_ptr, peer_pitch = frame_base + rank * width * 4, world * width * 4
 
     # kernels launched per step (the PHASED variant is four launches per frame)
     _, st0 = rt.Renderer.render_rows(opts, scene, row_start=row_start, row_stride=row_stride, row_count=my_rows,
@@ -229,6 +244,10 @@ def main():
     flush = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def step():
+        if peer:   # the traversal kernels' framebuffer stores ARE the gather (NVLink peer writes)
+            rt.Renderer.render_rows(opts, scene, row_start=row_start, row_stride=row_stride, row_count=my_rows,
+                                    out_ptr=peer_ptr, pitch=peer_pitch, stream=stream.cuda_stream)
+            return
         rt.Renderer.render_rows(opts, scene, row_start=row_start, row_stride=row_stride, row_count=my_rows,
                                 out_ptr=fb.data_ptr(), stream=stream.cuda_stream)
         if bands:
@@ -260,6 +279,19 @@ def main():
     barrier()
     wall_ms = (time.perf_counter() - w0) * 1e3
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+
+    peer_ok = None
+    if peer:
+        barrier()
+        if rank == 0:   # the gathered frame must equal a frame rendered by rank 0 alone
+            import numpy as _np
+            whole = torch.zeros((height, width, 4), dtype=torch.uint8, device="cuda")
+            rt.Renderer.render_rows(opts, scene, out_ptr=whole.data_ptr(), stream=stream.cuda_stream)
+            torch.cuda.synchronize()
+            got = rt.PinnedBuffer(height * width * 4)
+            rt.memcpy(got.ptr, frame_base, got.nbytes)
+            peer_ok = bool(_np.array_equal(got.array.reshape(height, width, 4), whole.cpu().numpy()))
+        barrier()
 
     # ---- e2e: the C-ABI call a user makes, every frame delivered to HOST memory ----------------
     # frames mode: rt_render_sweep (what `rtrace --frames` calls): the device-to-host copy of frame f
@@ -333,7 +365,8 @@ def main():
             "config": {
                 "workload": "%s: pyramid level %d (%d spheres) at %dx%d, %d spp" % (
                     args.workload, level, (4 ** level - 1) // 3, width, height, spp * spp),
-                "partition": ("interleaved row bands + NCCL gather to rank 0" if bands else
+                "partition": (("interleaved row bands; kernels store into rank 0's frame through IPC peer memory (NVLink)"
+                               if peer else "interleaved row bands + NCCL gather to rank 0") if bands else
                               "one whole frame per rank per step (frame-sharded sweep), no collective"),
                 "l2": "not flushed" if flush is None else "flushed between steps (256 MiB memset, outside the timed events)",
                 "rays_per_frame": {"primary": primary * (world if bands else 1), "shadow": None if bands else shadow},
@@ -355,6 +388,7 @@ def main():
                              "rt_render_sweep: per frame the kernel-parameter blocks (camera, options; 4 launches) go in "
                              "and the RGBA8 frame comes out to pinned host memory; copy of frame f overlaps render of f+1")},
             "gpu_launches": args.steps * world * launches_per_step,
+            "gathered_frame_verified": peer_ok,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

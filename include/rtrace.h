@@ -150,9 +150,10 @@ int rt_render_sweep(const rt_scene *s, const rt_camera *cameras, uint32_t n_fram
                     rt_frame_callback cb, void *user, rt_stats *stats);
 
 /* Whole frame on ngpu GPUs of this process (devices 0..ngpu-1): the scene is
- * replicated, rows are interleaved (GPU g renders rows g, g+ngpu, ...) and the
- * bands are gathered into GPU 0's frame by strided peer copies over NVLink, then
- * copied to rgba_out (host).  scenes[g] must live on device g.  Replaces the
+ * replicated, rows are interleaved (GPU g renders rows g, g+ngpu, ...) and every
+ * GPU's kernel stores its pixels directly into GPU 0's frame through peer memory
+ * (NVLink); without peer access the bands are gathered by strided copies.  The
+ * frame is then copied to rgba_out (host).  scenes[g] must live on device g.  Replaces the
  * thread pool + sync_channel of Renderer::render (render.rs:271-307). */
 int rt_render_frame_multi(rt_scene *const *scenes, int ngpu, const rt_camera *camera,
                           uint32_t width, uint32_t height, uint32_t spp,
@@ -184,6 +185,18 @@ int rt_microbench_fp32(int device, int mode, double *tflops);
  * ray-sphere distance and normalisation with the scalar ones, on n pseudo-random
  * inputs; all six mismatch counters must be 0. */
 int rt_selftest_math(uint32_t n, uint32_t seed, uint64_t mismatches[6]);
+
+/* Device memory on the current device, and CUDA IPC handles for it: how the ranks of a
+ * multi-process job (one process per GPU) hand rank 0's frame to the others, which then
+ * pass `frame + rank*width*4` with pitch `world*width*4` to rt_render_rows -- their kernels
+ * store the finished pixels straight into rank 0's HBM over NVLink (no gather step). */
+int rt_device_alloc(size_t bytes, void **out);
+void rt_device_free(void *p);
+int rt_ipc_export(const void *device_ptr, uint8_t handle[64]);
+int rt_ipc_open(const uint8_t handle[64], void **out);
+int rt_ipc_close(void *p);
+/* cudaMemcpy(dst, src, bytes, cudaMemcpyDefault) for buffers obtained above. */
+int rt_memcpy(void *dst, const void *src, size_t bytes);
 
 /* Pinned host memory for output buffers (what the CLI hands to rt_render_frame so
  * the device-to-host copy runs at full PCIe rate).  Replaces the Vec<u8> of

@@ -266,7 +266,10 @@ int launch(rt_scene *s, rt::RenderParams &p, bool diag, cudaStream_t stream) {
         if (rc != RT_OK) return rc;
         e = rt_launch_render_phased(diag, p, stream, tile_shape());
     } else if (v == RT_KERNEL_TILE) {
-        e = rt_launch_render_tile(diag, p, stream, tile_shape());
+        // AUTO picks the fused kernel only for small frames, where one independent warp per tile
+        // (shape 2) beats CTA-shared culls (warps waiting at barriers with too few CTAs to cover them)
+        static const char *force = getenv("RTRACE_TILE_SHAPE");
+        e = rt_launch_render_tile(diag, p, stream, (force && *force) ? atoi(force) : (g_variant == RT_VARIANT_AUTO ? 2 : 0));
     } else {
         e = rt_launch_render(v, diag, p, stream);
     }
@@ -458,8 +461,15 @@ static int render_rows_impl(rt_scene *s, const rt_camera *camera, uint32_t width
 
     int out_dev = -1;
     const bool out_on_device = rgba_out && is_device_ptr(rgba_out, &out_dev);
-    if (out_on_device && out_dev != s->device)
-        return fail(RT_ERR_INVALID, "rgba_out lives on device %d, the scene on device %d", out_dev, s->device);
+    if (out_on_device && out_dev != s->device) {
+        // a peer GPU's memory (e.g. rank 0's frame): the kernel stores over NVLink
+        int can = 0;
+        CUDA_TRY(cudaDeviceCanAccessPeer(&can, s->device, out_dev));
+        if (!can) return fail(RT_ERR_INVALID, "rgba_out lives on device %d, which device %d cannot access", out_dev, s->device);
+        cudaError_t pe = cudaDeviceEnablePeerAccess(out_dev, 0);
+        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) return fail(RT_ERR_CUDA, "enable peer access %d->%d: %s", s->device, out_dev, cudaGetErrorString(pe));
+        cudaGetLastError();
+    }
     if (out_on_device && (((uintptr_t)rgba_out) & 3)) return fail(RT_ERR_INVALID, "device rgba_out must be 4-byte aligned");
     int kinds_dev = -1;
     const bool kinds_on_device = kinds_out && is_device_ptr(kinds_out, &kinds_dev);
@@ -673,21 +683,24 @@ int rt_render_frame_multi(rt_scene *const *scenes, int ngpu, const rt_camera *ca
         rt_scene *s = scenes[g];
         DeviceGuard guard(s->device);
         if (!guard.ok) return fail(RT_ERR_CUDA, "cannot select device %d", s->device);
+        bool peer = g == 0;
         if (g > 0) {
             int can = 0;
-            CUDA_TRY(cudaDeviceCanAccessPeer(&can, root->device, s->device));
+            CUDA_TRY(cudaDeviceCanAccessPeer(&can, s->device, root->device));
             if (can) {
                 cudaError_t e = cudaDeviceEnablePeerAccess(root->device, 0);
                 if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(RT_ERR_CUDA, "enable peer %d->%d: %s", s->device, root->device, cudaGetErrorString(e));
                 cudaGetLastError();
+                peer = true;
             }
         }
         const uint32_t rows = (height > (uint32_t)g) ? (height - g + ngpu - 1) / ngpu : 0;
         if (rows == 0) continue;
         rt::RenderParams p;
         fill_params(s, camera, width, height, spp, (uint32_t)g, (uint32_t)ngpu, rows, p);
-        if (g == 0) {
-            p.out = frame;  // rows 0, G, 2G, ... in place
+        if (peer) {
+            // rows g, g+G, ... written in place: GPU g's stores land in GPU 0's frame over NVLink
+            p.out = frame + row_bytes * g;
             p.pitch = row_bytes * ngpu;
         } else {
             int rc = ensure(&s->d_fb, &s->d_fb_cap, row_bytes * rows);
@@ -701,7 +714,7 @@ int rt_render_frame_multi(rt_scene *const *scenes, int ngpu, const rt_camera *ca
             if (rc != RT_OK) return rc;
         }
         if (stats) CUDA_TRY(cudaEventRecord(s->ev1, s->own_stream));
-        if (g > 0)  // strided peer copy over NVLink: the pitch de-interleaves the band into the frame
+        if (!peer)  // no peer access: strided copy, the pitch de-interleaves the band into the frame
             CUDA_TRY(cudaMemcpy2DAsync(frame + row_bytes * g, row_bytes * ngpu, s->d_fb, row_bytes, row_bytes, rows, cudaMemcpyDefault, s->own_stream));
     }
     double kmax = 0.0;
@@ -811,6 +824,48 @@ int rt_measure_fp32_peak(int device, double *tflops, double *sm_clock_mhz) {
         // effective clock implied by the measured rate: 128 FFMA lanes per SM per cycle
         *sm_clock_mhz = *tflops * 1e12 / (2.0 * 128.0 * prop.multiProcessorCount) / 1e6;
     }
+    return RT_OK;
+}
+
+int rt_device_alloc(size_t bytes, void **out) {
+    if (!out) return fail(RT_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (rt_device_count() == 0) return fail(RT_ERR_CUDA, "no CUDA device");
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) return fail(RT_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return RT_OK;
+}
+
+void rt_device_free(void *p) {
+    if (p) cudaFree(p);
+}
+
+int rt_ipc_export(const void *device_ptr, uint8_t handle[64]) {
+    if (!device_ptr || !handle) return fail(RT_ERR_INVALID, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, const_cast<void *>(device_ptr)));
+    memcpy(handle, &h, 64);
+    return RT_OK;
+}
+
+int rt_ipc_open(const uint8_t handle[64], void **out) {
+    if (!handle || !out) return fail(RT_ERR_INVALID, "NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return RT_OK;
+}
+
+int rt_ipc_close(void *p) {
+    if (!p) return RT_OK;
+    CUDA_TRY(cudaIpcCloseMemHandle(p));
+    return RT_OK;
+}
+
+int rt_memcpy(void *dst, const void *src, size_t bytes) {
+    if (!dst || !src) return fail(RT_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
     return RT_OK;
 }
 

@@ -382,7 +382,11 @@ __global__ void __launch_bounds__(32 * CW * CH, RT_PHASED_MINBLOCKS) phase_shade
         }
     } else if (lane_in) {
         const V3x2 eye2 = v3x2s(eye), light2 = v3x2s(light), to_light2 = v3x2s(to_light);
-#pragma unroll 1
+#ifndef RT_K4_UNROLL
+#define RT_K4_UNROLL 1
+#endif
+        constexpr int K4_UNROLL = RT_K4_UNROLL;
+#pragma unroll K4_UNROLL
         for (int s0 = 0; s0 < S; s0 += 2) {  // two slots per pass: packed f32x2 arithmetic
             const int s1 = (s0 + 1 < S) ? s0 + 1 : s0;
             uint32_t x0, j0, x1, j1;

@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "rt_scene_counts", "rt_scene_export_nodes", "rt_flatten_pyramid_host", "rt_scene_light", "rt_scene_eye",
     "rt_scene_device", "rt_render_region", "rt_render_rows", "rt_render_frame", "rt_render_sweep",
     "rt_render_frame_multi",
-    "rt_count_rays", "rt_trace_rays", "rt_measure_fp32_peak", "rt_microbench_fp32", "rt_selftest_math", "rt_host_alloc", "rt_host_free",
+    "rt_count_rays", "rt_trace_rays", "rt_measure_fp32_peak", "rt_microbench_fp32", "rt_selftest_math", "rt_host_alloc", "rt_host_free", "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_memcpy",
 ]
 
 
@@ -87,6 +87,13 @@ def lib():
     L.rt_microbench_fp32.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
     L.rt_selftest_math.argtypes = [u32, u32, u64p]
     L.rt_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.rt_device_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.rt_device_free.argtypes = [vp]
+    L.rt_device_free.restype = None
+    L.rt_ipc_export.argtypes = [vp, C.c_char_p]
+    L.rt_ipc_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.rt_ipc_close.argtypes = [vp]
+    L.rt_memcpy.argtypes = [vp, vp, C.c_size_t]
     L.rt_host_free.argtypes = [vp]
     L.rt_host_free.restype = None
     _lib = L
@@ -337,6 +344,36 @@ def selftest_math(n=1 << 24, seed=1):
     m = (C.c_uint64 * 6)()
     _check(lib().rt_selftest_math(n, seed, m))
     return tuple(int(v) for v in m)
+
+
+def device_alloc(nbytes):
+    p = C.c_void_p()
+    _check(lib().rt_device_alloc(nbytes, C.byref(p)))
+    return p.value
+
+
+def device_free(ptr):
+    lib().rt_device_free(C.c_void_p(ptr))
+
+
+def ipc_export(ptr):
+    h = C.create_string_buffer(64)
+    _check(lib().rt_ipc_export(C.c_void_p(ptr), h))
+    return h.raw
+
+
+def ipc_open(handle):
+    p = C.c_void_p()
+    _check(lib().rt_ipc_open(C.create_string_buffer(handle, 64), C.byref(p)))
+    return p.value
+
+
+def memcpy(dst, src, nbytes):
+    _check(lib().rt_memcpy(C.c_void_p(dst), C.c_void_p(src), nbytes))
+
+
+def ipc_close(ptr):
+    _check(lib().rt_ipc_close(C.c_void_p(ptr)))
 
 
 class PinnedBuffer:
