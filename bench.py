@@ -160,8 +160,8 @@ def run_reference(args, width, height, spp, level):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": done,
         "warmup": min(args.warmup, 1), "ms_per_step": secs / done * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "width": width, "height": height, "spp": spp, "level": level,
-                   "scene": "pyramid level %d" % level},
+        "config": {"workload": "%s: pyramid level %d (%d spheres) at %dx%d, %d spp" % (
+            args.workload, level, (4 ** level - 1) // 3, width, height, spp * spp)},
         "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
