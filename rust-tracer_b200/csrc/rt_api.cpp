@@ -239,11 +239,14 @@ int prepare_phased(rt_scene *s, rt::RenderParams &p, cudaStream_t stream) {
     size_t wb = 0, hb = 0;
     uint32_t units = 0;
     rt_phased_scratch(p.width, p.row_count, p.spp, tile_shape(), &wb, &hb, &units);
+    if (const char *cap = getenv("RTRACE_POOL_UNITS")) {  // tests: a tiny pool exercises the overflow fallback
+        if (*cap) units = (uint32_t)strtoul(cap, nullptr, 10);
+    }
     std::lock_guard<std::mutex> lock(s->mu_phased);
     rt_scene::Phased &ph = s->phased[stream];
     int rc = ensure_typed(&ph.winner, &ph.winner_cap, wb);
     if (rc == RT_OK) rc = ensure_typed(&ph.hdr, &ph.hdr_cap, hb);
-    if (rc == RT_OK && ph.pool_units < units) {
+    if (rc == RT_OK && ph.pool_units != units && (ph.pool_units < units || getenv("RTRACE_POOL_UNITS"))) {
         size_t cap = (size_t)ph.pool_units * sizeof(uint4);
         rc = ensure_typed(&ph.pool, &cap, (size_t)units * sizeof(uint4));
         if (rc == RT_OK) ph.pool_units = units;

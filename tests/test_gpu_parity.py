@@ -203,3 +203,40 @@ def test_auto_picks_a_variant_for_every_regime(rt, oracle):
         img = rt.Renderer.render(rt.RenderOptions(w, h, spp), gs)
         ref, _ = os_.render(w, h, spp)
         assert_same(img, ref, "auto %dx%d spp %d L%d" % (w, h, spp, level))
+
+
+def test_candidate_pool_overflow_falls_back_to_the_lane_walk(rt, oracle_scene8, gpu_scene8):
+    """A cull tile whose candidates do not fit the pool is rendered by the per-lane walk: same bytes."""
+    w, h, spp = 512, 288, 1
+    ref, _ = oracle_scene8.render(w, h, spp)
+    rt.set_variant(rt.VARIANT_PHASED)
+    try:
+        for units in ("64", "600", "3000"):   # nothing fits / some tiles fit / most tiles fit
+            os.environ["RTRACE_POOL_UNITS"] = units
+            img, kinds = rt.Renderer.render_rows(rt.RenderOptions(w, h, spp), gpu_scene8, kinds=True)
+            assert_same(img, ref, "pool of %s units" % units)
+    finally:
+        os.environ.pop("RTRACE_POOL_UNITS", None)
+        rt.set_variant(rt.VARIANT_AUTO)
+    img = rt.Renderer.render(rt.RenderOptions(w, h, spp), gpu_scene8)   # pool back to its normal size
+    assert_same(img, ref)
+
+
+def test_c4_sized_frame_agrees_with_the_exact_lane_walk(rt):
+    """BASELINE C4 (7680x4320, 4x4, level 9): bands of the candidate-list frame equal the per-lane walk,
+    which is the reference recursion restated (and is itself checked against the oracle above)."""
+    w, h, spp = 7680, 4320, 4
+    gs = rt.Scene(level=9)
+    o = rt.RenderOptions(w, h, spp)
+    rt.set_variant(rt.VARIANT_AUTO)
+    full = rt.Renderer.render(o, gs)
+    rt.set_variant(rt.VARIANT_LANE)
+    try:
+        for y0 in (1200, 2177, 3900):
+            band = rt.Renderer.render_rows(o, gs, row_start=y0, row_stride=1, row_count=24)
+            assert np.array_equal(band, full[y0:y0 + 24]), "rows %d.." % y0
+    finally:
+        rt.set_variant(rt.VARIANT_AUTO)
+    # interleaved partition of the big frame (what 8 GPUs would each render)
+    part = rt.Renderer.render_rows(o, gs, row_start=5, row_stride=8)
+    assert np.array_equal(part, full[5::8])
