@@ -220,25 +220,32 @@ __global__ void __launch_bounds__(32 * CW * CH, RT_PHASED_MINBLOCKS) phase_test_
                                           p.row_start + j1 * p.row_stride, s1 % NS);
             F2 bd = f2s(RT_INF);
             uint32_t bi0 = NO_HIT, bi1 = NO_HIT;
+            auto test = [&](const uint4 u0, const uint4 u1, const uint4 u2) {
+                V3x2 v;
+                v.x = f2(__uint_as_float(u0.x), __uint_as_float(u0.y));
+                v.y = f2(__uint_as_float(u0.z), __uint_as_float(u0.w));
+                v.z = f2(__uint_as_float(u1.x), __uint_as_float(u1.y));
+                const F2 nvv = f2(__uint_as_float(u1.z), __uint_as_float(u1.w));
+                const F2 rr = f2(__uint_as_float(u2.x), __uint_as_float(u2.y));
+                const uint32_t idx = u2.z;
+                const F2 dist = primary_distance2(one, v, nvv, rr, d);
+                // primitive.rs:79 + pre-order visiting: strictly closer wins, ties -> lowest index
+                if (dist.x < bd.x || (dist.x == bd.x && idx < bi0 && bi0 != NO_HIT)) bd.x = dist.x, bi0 = idx;
+                if (dist.y < bd.y || (dist.y == bd.y && idx < bi1 && bi1 != NO_HIT)) bd.y = dist.y, bi1 = idx;
+            };
+            // hot path: the first 32 candidates of the staged chunk, straight from shared memory
+            for (uint32_t m = mask0; m; m &= m - 1u) {
+                const uint32_t c = (uint32_t)__ffs((int)m) - 1u;
+                test(stage[1u + 3u * c], stage[2u + 3u * c], stage[3u + 3u * c]);
+            }
+            // cold path: the rest of the staged chunk and any further chunks of the chain
             for (uint32_t base = head; base != NO_CHUNK;) {
                 const uint4 hdr = fetch(base, 0u);
                 const uint32_t n = hdr.x;
-                for (uint32_t c0 = 0; c0 < n; c0 += 32) {
-                    const uint32_t mask = (base == head && c0 == 0) ? mask0 : chunk_mask(base, c0, min(n, c0 + 32u));
-                    for (uint32_t m = mask; m; m &= m - 1u) {
+                for (uint32_t c0 = (base == head) ? 32u : 0u; c0 < n; c0 += 32) {
+                    for (uint32_t m = chunk_mask(base, c0, min(n, c0 + 32u)); m; m &= m - 1u) {
                         const uint32_t c = c0 + (uint32_t)__ffs((int)m) - 1u;
-                        const uint4 u0 = fetch(base, 1u + 3u * c), u1 = fetch(base, 2u + 3u * c), u2 = fetch(base, 3u + 3u * c);
-                        V3x2 v;
-                        v.x = f2(__uint_as_float(u0.x), __uint_as_float(u0.y));
-                        v.y = f2(__uint_as_float(u0.z), __uint_as_float(u0.w));
-                        v.z = f2(__uint_as_float(u1.x), __uint_as_float(u1.y));
-                        const F2 nvv = f2(__uint_as_float(u1.z), __uint_as_float(u1.w));
-                        const F2 rr = f2(__uint_as_float(u2.x), __uint_as_float(u2.y));
-                        const uint32_t idx = u2.z;
-                        const F2 dist = primary_distance2(one, v, nvv, rr, d);
-                        // primitive.rs:79 + pre-order visiting: strictly closer wins, ties -> lowest index
-                        if (dist.x < bd.x || (dist.x == bd.x && idx < bi0 && bi0 != NO_HIT)) bd.x = dist.x, bi0 = idx;
-                        if (dist.y < bd.y || (dist.y == bd.y && idx < bi1 && bi1 != NO_HIT)) bd.y = dist.y, bi1 = idx;
+                        test(fetch(base, 1u + 3u * c), fetch(base, 2u + 3u * c), fetch(base, 3u + 3u * c));
                     }
                 }
                 base = hdr.y;
@@ -359,7 +366,6 @@ __global__ void __launch_bounds__(32 * CW * CH, RT_PHASED_MINBLOCKS) phase_shade
     }
     __syncthreads();
     if (pt_x >= geo.ptiles_x || pt_y >= geo.ptiles_y) return;  // cull tile on the frame edge
-    auto fetch = [&](uint32_t base, uint32_t off) { return base == head ? stage[off] : __ldg(&p.pool[base + off]); };
     unsigned n_hits = 0, n_shadow = 0;
     V3 c = v3(0.0f, 0.0f, 0.0f);  // colour / alpha of the pixel being accumulated (render.rs:233-234)
     float alpha = 0.0f;
@@ -425,31 +431,38 @@ __global__ void __launch_bounds__(32 * CW * CH, RT_PHASED_MINBLOCKS) phase_shade
                 }
                 pend = 0;
             }
-            for (uint32_t base = head; base < OVERFLOWED && pend;) {
-                const uint4 hdr = fetch(base, 0u);
-                for (uint32_t ci = 0; ci < hdr.x && pend; ci++) {
-                    const uint4 u0 = fetch(base, 1u + 2u * ci), u1 = fetch(base, 2u + 2u * ci);
-                    V3x2 cc;
-                    cc.x = f2(__uint_as_float(u0.x), __uint_as_float(u0.y));
-                    cc.y = f2(__uint_as_float(u0.z), __uint_as_float(u0.w));
-                    cc.z = f2(__uint_as_float(u1.x), __uint_as_float(u1.y));
-                    const F2 rr = f2(__uint_as_float(u1.z), __uint_as_float(u1.w));
-                    // primitive.rs:56-58 for the shadow rays {pos: o, dir: -light}
-                    const V3x2 sv = vadd2(one, cc, no);  // center - ray.pos
-                    const F2 b = vdot2(one, sv, to_light2);
-                    const F2 disc = f2add(one, f2sub(one, f2mul(b, b), vdot2(one, sv, sv)), rr);
-                    // finite iff disc >= 0 and !(b + sqrt(disc) < 0) (primitive.rs:60-68); b >= 0 settles the latter
-                    bool f0 = !(disc.x < 0.0f), f1 = !(disc.y < 0.0f);
-                    if ((f0 && b.x < 0.0f) || (f1 && b.y < 0.0f)) {
-                        const F2 t2 = f2add(one, b, fsqrt_nr2(disc));
-                        f0 = f0 && !(t2.x < 0.0f);
-                        f1 = f1 && !(t2.y < 0.0f);
-                    }
-                    const uint32_t f = ((f0 ? 1u : 0u) | (f1 ? 2u : 0u)) & pend;
-                    pend &= ~f;
-                    occluded |= f;
+            auto shadow_test = [&](const uint4 u0, const uint4 u1) {
+                V3x2 cc;
+                cc.x = f2(__uint_as_float(u0.x), __uint_as_float(u0.y));
+                cc.y = f2(__uint_as_float(u0.z), __uint_as_float(u0.w));
+                cc.z = f2(__uint_as_float(u1.x), __uint_as_float(u1.y));
+                const F2 rr = f2(__uint_as_float(u1.z), __uint_as_float(u1.w));
+                // primitive.rs:56-58 for the shadow rays {pos: o, dir: -light}
+                const V3x2 sv = vadd2(one, cc, no);  // center - ray.pos
+                const F2 b = vdot2(one, sv, to_light2);
+                const F2 disc = f2add(one, f2sub(one, f2mul(b, b), vdot2(one, sv, sv)), rr);
+                // finite iff disc >= 0 and !(b + sqrt(disc) < 0) (primitive.rs:60-68); b >= 0 settles the latter
+                bool f0 = !(disc.x < 0.0f), f1 = !(disc.y < 0.0f);
+                if ((f0 && b.x < 0.0f) || (f1 && b.y < 0.0f)) {
+                    const F2 t2 = f2add(one, b, fsqrt_nr2(disc));
+                    f0 = f0 && !(t2.x < 0.0f);
+                    f1 = f1 && !(t2.y < 0.0f);
                 }
-                base = hdr.y;
+                const uint32_t f = ((f0 ? 1u : 0u) | (f1 ? 2u : 0u)) & pend;
+                pend &= ~f;
+                occluded |= f;
+            };
+            if (head < OVERFLOWED) {
+                // hot path: the staged chunk, straight from shared memory
+                const uint32_t n0 = stage[0].x;
+                for (uint32_t ci = 0; ci < n0 && pend; ci++) shadow_test(stage[1u + 2u * ci], stage[2u + 2u * ci]);
+                // cold path: further chunks of the chain
+                for (uint32_t base = stage[0].y; base != NO_CHUNK && pend;) {
+                    const uint4 hdr = __ldg(&p.pool[base]);
+                    for (uint32_t ci = 0; ci < hdr.x && pend; ci++)
+                        shadow_test(__ldg(&p.pool[base + 1u + 2u * ci]), __ldg(&p.pool[base + 2u + 2u * ci]));
+                    base = hdr.y;
+                }
             }
             // accumulate in reference sample order (render.rs:236-250), quantise, store (render.rs:92-109)
 #pragma unroll
@@ -542,7 +555,7 @@ void rt_phased_scratch(uint32_t width, uint32_t rows, uint32_t spp, int shape, s
     }
     switch (spp) {
         case 1:
-            if (shape == 1) RT_GEO(1, 2, 2, 4, 4) else RT_GEO(1, 2, 2, 2, 2)
+            if (shape == 1) RT_GEO(1, 2, 2, 4, 4) else if (shape == 2) RT_GEO(1, 4, 2, 1, 2) else if (shape == 3) RT_GEO(1, 2, 1, 2, 4) else if (shape == 4) RT_GEO(1, 2, 1, 1, 2) else RT_GEO(1, 2, 2, 2, 2)
             break;
         case 2:
             if (shape == 1) RT_GEO(2, 1, 1, 4, 4) else RT_GEO(2, 1, 1, 2, 2)
@@ -567,6 +580,9 @@ cudaError_t rt_launch_render_phased(bool diag, const RenderParams &p, cudaStream
     // shape 0: cull tile = 2x2 pixel tiles; shape 1: 4x4 pixel tiles
     switch (p.spp) {
         case 1:
+            if (shape == 2) return launch_phased<1, 4, 2, 1, 2>(diag, p, stream);  // 8 pixels per lane
+            if (shape == 3) return launch_phased<1, 2, 1, 2, 4>(diag, p, stream);  // 2 pixels per lane, 32x16 cull tile
+            if (shape == 4) return launch_phased<1, 2, 1, 1, 2>(diag, p, stream);  // 2 pixels per lane, 16x8 cull tile
             return shape == 1 ? launch_phased<1, 2, 2, 4, 4>(diag, p, stream) : launch_phased<1, 2, 2, 2, 2>(diag, p, stream);
         case 2:
             return shape == 1 ? launch_phased<2, 1, 1, 4, 4>(diag, p, stream) : launch_phased<2, 1, 1, 2, 2>(diag, p, stream);
