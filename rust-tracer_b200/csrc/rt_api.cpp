@@ -146,6 +146,7 @@ void fill_params(const rt_scene *s, const rt_camera *cam, uint32_t w, uint32_t h
     p.level = s->flat.level;
     p.leaf_rmin = s->flat.leaf_rmin;
     for (int k = 0; k < 3; k++) p.scene_center[k] = s->flat.sph.empty() ? 0.0f : s->flat.sph[k];
+    p.scene_radius = s->flat.sph.empty() ? 0.0f : s->flat.sph[3];
     const float *eye = cam ? cam->eye : s->flat.eye;
     for (int k = 0; k < 3; k++) {
         p.eye[k] = eye[k];
@@ -192,8 +193,19 @@ bool orthonormal(const float b[9]) {
 // AUTO, TILE and PHASED apply to regular pyramids with spp 1..4 and an orthonormal
 // camera; anything else falls back to the per-lane walk.  All variants produce
 // identical bytes.
+// The candidate-list variants compute min over leaves, which equals the reference's pruned
+// pre-order walk only while the eye is OUTSIDE every group bound: for an origin inside a bound
+// `distance_from_ray` returns the exit distance (primitive.rs:70-71), so `bound >= hit.distance`
+// (group.rs:73) may prune a subtree that holds a closer leaf -- an order-dependent result that
+// only the per-lane walk reproduces.  All bounds lie inside the root bound, so one test suffices.
+bool eye_outside_root_bound(const rt::RenderParams &p) {
+    const float dx = p.eye[0] - p.scene_center[0], dy = p.eye[1] - p.scene_center[1], dz = p.eye[2] - p.scene_center[2];
+    const float d2 = dx * dx + dy * dy + dz * dz, r = p.scene_radius * 1.0005f + 1e-4f;
+    return d2 > r * r;
+}
+
 int kernel_variant(const rt::RenderParams &p) {
-    const bool tile_ok = rt_tile_supported(p) && (!p.has_basis || orthonormal(p.basis));
+    const bool tile_ok = rt_tile_supported(p) && (!p.has_basis || orthonormal(p.basis)) && eye_outside_root_bound(p);
     switch (g_variant) {
         case RT_VARIANT_LANE:
             return RT_KERNEL_LANE;

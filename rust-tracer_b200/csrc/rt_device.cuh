@@ -82,6 +82,7 @@ struct RenderParams {
     uint32_t level;  // pyramid level (regular tree: child offsets follow from the depth); 0 = hand-built tree
     float leaf_rmin;  // smallest leaf radius (regular pyramid)
     float scene_center[3];  // centre of the root bound (host-side heuristics only)
+    float scene_radius;     // radius of the root bound
     float one;             // 1.0f, deliberately a runtime value (rt_pack.cuh)
     uint32_t tile_stride;  // TILE variant: warp w renders tile (w * tile_stride) mod n_tiles
     float eye[3];

@@ -240,3 +240,44 @@ def test_c4_sized_frame_agrees_with_the_exact_lane_walk(rt):
     # interleaved partition of the big frame (what 8 GPUs would each render)
     part = rt.Renderer.render_rows(o, gs, row_start=5, row_stride=8)
     assert np.array_equal(part, full[5::8])
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("light_along_view", dict(light=(0.0, 0.0, -1.0))),          # shadow rays parallel to the view axis: degenerate strip
+    ("light_from_below", dict(light=(0.3, 2.0, 0.5))),
+    ("light_sideways", dict(light=(-4.0, -0.2, 0.1))),
+    ("eye_close", dict(eye=(0.4, 0.2, -2.2))),
+    ("eye_inside_root_bound", dict(eye=(0.1, -0.2, -1.6))),
+    ("eye_far_off_axis", dict(eye=(3.0, 1.5, -9.0))),
+    ("scaled_shifted_scene", dict(origin=(0.7, -0.4, 0.3), radius=0.6)),
+    ("big_scene", dict(origin=(0.0, -2.0, 4.0), radius=2.5, eye=(0.0, 0.0, -6.0))),
+])
+def test_other_scenes_match_oracle(rt, oracle, name, kw):
+    """Scene::default is one point in the parameter space; the culling geometry must stay conservative
+    for any light, eye and scene placement (every variant, byte for byte, plus the per-sample mask)."""
+    level, w, h, spp = 6, 224, 126, 2
+    gs, os_ = rt.Scene(level=level, **kw), oracle.Scene(level=level, **kw)
+    ref, okinds, ctr = os_.render_region(w, h, spp, 0, 0, w, h, kinds=True)
+    try:
+        for v in variants(rt):
+            rt.set_variant(v)
+            img, kinds = rt.Renderer.render_rows(rt.RenderOptions(w, h, spp), gs, kinds=True)
+            assert np.array_equal(kinds, okinds), "%s: mask differs for variant %d" % (name, v)
+            assert_same(img, ref, "%s variant %d" % (name, v))
+    finally:
+        rt.set_variant(rt.VARIANT_AUTO)
+    assert ctr.primary_hits > 0
+
+
+def test_other_scenes_at_high_resolution(rt, oracle):
+    """The same at a resolution where the tiles are small against the spheres (PHASED regime)."""
+    kw = dict(light=(0.0, 0.0, -1.0), eye=(0.5, 0.3, -3.0))
+    gs, os_ = rt.Scene(level=7, **kw), oracle.Scene(level=7, **kw)
+    w, h, spp = 1920, 1080, 1
+    ref, _ = os_.render(w, h, spp)
+    try:
+        for v in (rt.VARIANT_TILE, rt.VARIANT_PHASED):
+            rt.set_variant(v)
+            assert_same(rt.Renderer.render(rt.RenderOptions(w, h, spp), gs), ref, "variant %d" % v)
+    finally:
+        rt.set_variant(rt.VARIANT_AUTO)
