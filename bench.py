@@ -311,7 +311,7 @@ def main():
                 rt.Renderer.render_rows(opts, scene, row_start=row_start, row_stride=row_stride, row_count=my_rows,
                                         out_ptr=pinned.ptr)
         else:
-            rt.Renderer.render_sweep(opts, scene, n, on_frame=on_frame)
+            rt.Renderer.render_sweep(opts, scene, n, on_frame=on_frame, rgb=True)
 
     e2e_run(3)
     barrier()
@@ -383,10 +383,13 @@ def main():
                         "note": "algorithmic HBM bytes = framebuffer written once (4 B/pixel); peak = MEASURED_PEAKS.json hbm_gbs" if peaks else "peak = fallback 6.65 TB/s"},
             },
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 512,
-                    "d2h_bytes_per_step": fb_bytes, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                    "d2h_bytes_per_step": fb_bytes if bands else fb_bytes // 4 * 3, "steps": e2e_steps,
+                    "ms_per_step": e2e_ms / e2e_steps,
                     "note": ("rt_render_rows -> pinned host buffer, synchronous" if bands else
-                             "rt_render_sweep: per frame the kernel-parameter blocks (camera, options; 4 launches) go in "
-                             "and the RGBA8 frame comes out to pinned host memory; copy of frame f overlaps render of f+1")},
+                             "rt_render_sweep_rgb (what `rtrace --frames` calls): per frame the kernel-parameter blocks "
+                             "(camera, options) go in and the RGB8 frame -- the body of the reference's P6 file, its sink "
+                             "drops alpha (render.rs:389-397) -- comes out to pinned host memory; copy of frame f "
+                             "overlaps the render of frame f+1")},
             "gpu_launches": args.steps * world * launches_per_step,
             "gathered_frame_verified": peer_ok,
             "clocks": clocks,

@@ -149,6 +149,13 @@ int rt_render_sweep(const rt_scene *s, const rt_camera *cameras, uint32_t n_fram
                     uint32_t width, uint32_t height, uint32_t spp,
                     rt_frame_callback cb, void *user, rt_stats *stats);
 
+/* The same sweep delivering RGB8 frames (width*height*3 bytes): the reference's sink drops the
+ * alpha channel anyway (render.rs:389-397), so the frame is packed on the device and a quarter of
+ * the PCIe traffic is saved.  The bytes are exactly the body of the P6 file. */
+int rt_render_sweep_rgb(const rt_scene *s, const rt_camera *cameras, uint32_t n_frames,
+                        uint32_t width, uint32_t height, uint32_t spp,
+                        rt_frame_callback cb, void *user, rt_stats *stats);
+
 /* Whole frame on ngpu GPUs of this process (devices 0..ngpu-1): the scene is
  * replicated, rows are interleaved (GPU g renders rows g, g+ngpu, ...) and every
  * GPU's kernel stores its pixels directly into GPU 0's frame through peer memory

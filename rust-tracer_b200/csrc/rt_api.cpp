@@ -54,6 +54,7 @@ struct rt_scene {
     // rt_render_sweep: double-buffered frames and the copy stream
     uint8_t *sweep_dev[2] = {nullptr, nullptr};
     uint8_t *sweep_host[2] = {nullptr, nullptr};
+    uint8_t *sweep_rgb[2] = {nullptr, nullptr};
     size_t sweep_bytes = 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t sweep_rendered[2] = {nullptr, nullptr}, sweep_copied[2] = {nullptr, nullptr};
@@ -390,6 +391,7 @@ void rt_scene_destroy(rt_scene *s) {
         if (s->own_stream) cudaStreamDestroy(s->own_stream);
         for (int k = 0; k < 2; k++) {
             if (s->sweep_dev[k]) cudaFree(s->sweep_dev[k]);
+            if (s->sweep_rgb[k]) cudaFree(s->sweep_rgb[k]);
             if (s->sweep_host[k]) cudaFreeHost(s->sweep_host[k]);
             if (s->sweep_rendered[k]) cudaEventDestroy(s->sweep_rendered[k]);
             if (s->sweep_copied[k]) cudaEventDestroy(s->sweep_copied[k]);
@@ -604,8 +606,8 @@ int rt_render_frame(const rt_scene *s, const rt_camera *camera, uint32_t width, 
                             nullptr, stats, nullptr, nullptr);
 }
 
-int rt_render_sweep(const rt_scene *cs, const rt_camera *cameras, uint32_t n_frames, uint32_t width, uint32_t height,
-                    uint32_t spp, rt_frame_callback cb, void *user, rt_stats *stats) {
+static int sweep_impl(const rt_scene *cs, const rt_camera *cameras, uint32_t n_frames, uint32_t width, uint32_t height,
+                      uint32_t spp, rt_frame_callback cb, void *user, rt_stats *stats, bool rgb) {
     rt_scene *s = const_cast<rt_scene *>(cs);
     int rc = check_frame_args(s, width, height, spp, 0, 1, height);
     if (rc != RT_OK) return rc;
@@ -616,6 +618,7 @@ int rt_render_sweep(const rt_scene *cs, const rt_camera *cameras, uint32_t n_fra
     std::lock_guard<std::mutex> lock(s->mu);
     const double t0 = now_ms();
     const size_t row_bytes = (size_t)width * 4, frame_bytes = row_bytes * height;
+    const size_t out_bytes = rgb ? (size_t)width * height * 3 : frame_bytes;
     // two device frames + two pinned host frames: the copy of frame f overlaps the render of f+1
     if (s->sweep_bytes < frame_bytes) {
         for (int k = 0; k < 2; k++) {
@@ -625,7 +628,10 @@ int rt_render_sweep(const rt_scene *cs, const rt_camera *cameras, uint32_t n_fra
         }
         s->sweep_bytes = 0;
         for (int k = 0; k < 2; k++) {
+            if (s->sweep_rgb[k]) cudaFree(s->sweep_rgb[k]);
+            s->sweep_rgb[k] = nullptr;
             CUDA_TRY(cudaMalloc(&s->sweep_dev[k], frame_bytes));
+            CUDA_TRY(cudaMalloc(&s->sweep_rgb[k], frame_bytes / 4 * 3 + 16));
             CUDA_TRY(cudaHostAlloc((void **)&s->sweep_host[k], frame_bytes, cudaHostAllocPortable));
         }
         s->sweep_bytes = frame_bytes;
@@ -649,15 +655,19 @@ int rt_render_sweep(const rt_scene *cs, const rt_camera *cameras, uint32_t n_fra
             rc = launch(s, p, false, s->own_stream);
             if (rc != RT_OK) return rc;
             launches += (uint32_t)launches_per_frame(p);
+            if (rgb) {  // the sink only needs RGB: pack on the device, copy 3 bytes per pixel
+                CUDA_TRY(rt_launch_pack_rgb(s->sweep_dev[k], s->sweep_rgb[k], (size_t)width * height, s->own_stream));
+                launches += 1;
+            }
             CUDA_TRY(cudaEventRecord(s->sweep_rendered[k], s->own_stream));
             CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->sweep_rendered[k], 0));
-            CUDA_TRY(cudaMemcpyAsync(s->sweep_host[k], s->sweep_dev[k], frame_bytes, cudaMemcpyDeviceToHost, s->copy_stream));
+            CUDA_TRY(cudaMemcpyAsync(s->sweep_host[k], rgb ? s->sweep_rgb[k] : s->sweep_dev[k], out_bytes, cudaMemcpyDeviceToHost, s->copy_stream));
             CUDA_TRY(cudaEventRecord(s->sweep_copied[k], s->copy_stream));
         }
         if (f >= 1) {  // hand frame f-1 to the caller while frame f renders
             const int k = (int)((f - 1) & 1u);
             CUDA_TRY(cudaEventSynchronize(s->sweep_copied[k]));
-            if (cb) cb(user, f - 1, s->sweep_host[k], frame_bytes);
+            if (cb) cb(user, f - 1, s->sweep_host[k], out_bytes);
         }
     }
     if (stats) {
@@ -667,6 +677,16 @@ int rt_render_sweep(const rt_scene *cs, const rt_camera *cameras, uint32_t n_fra
         stats->gpus = 1;
     }
     return RT_OK;
+}
+
+int rt_render_sweep(const rt_scene *s, const rt_camera *cameras, uint32_t n_frames, uint32_t width, uint32_t height,
+                    uint32_t spp, rt_frame_callback cb, void *user, rt_stats *stats) {
+    return sweep_impl(s, cameras, n_frames, width, height, spp, cb, user, stats, false);
+}
+
+int rt_render_sweep_rgb(const rt_scene *s, const rt_camera *cameras, uint32_t n_frames, uint32_t width, uint32_t height,
+                        uint32_t spp, rt_frame_callback cb, void *user, rt_stats *stats) {
+    return sweep_impl(s, cameras, n_frames, width, height, spp, cb, user, stats, true);
 }
 
 int rt_render_frame_multi(rt_scene *const *scenes, int ngpu, const rt_camera *camera, uint32_t width, uint32_t height,

@@ -191,6 +191,25 @@ __global__ void trace_rays_kernel(const float4 *__restrict__ sph, const uint32_t
     hits[i * 4 + 3] = nrm.z;
 }
 
+// RGBA8 -> RGB8 (the PPM sink drops alpha, render.rs:389-397): 4 pixels per thread, 16 bytes in, 12 out.
+__global__ void pack_rgb_kernel(const uint32_t *__restrict__ rgba, uint32_t *__restrict__ rgb, size_t n_quads,
+                                size_t n_px) {
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n_quads) {
+        const uint4 v = reinterpret_cast<const uint4 *>(rgba)[q];
+        const uint32_t a = v.x & 0xffffffu, b = v.y & 0xffffffu, c = v.z & 0xffffffu, d = v.w & 0xffffffu;
+        rgb[3 * q + 0] = a | (b << 24);
+        rgb[3 * q + 1] = (b >> 8) | (c << 16);
+        rgb[3 * q + 2] = (c >> 16) | (d << 8);
+    }
+    if (q == 0) {  // up to 3 trailing pixels
+        uint8_t *o = reinterpret_cast<uint8_t *>(rgb);
+        const uint8_t *i = reinterpret_cast<const uint8_t *>(rgba);
+        for (size_t px = n_quads * 4; px < n_px; px++)
+            for (int k = 0; k < 3; k++) o[px * 3 + k] = i[px * 4 + k];
+    }
+}
+
 // Register-resident FP32 chains: the live roofline denominator.
 // mode 0: FFMA; mode 1: alternating FMUL / FADD (the unfused mix the parity rule forces);
 // mode 2: packed FFMA2 (sm_100 f32x2); mode 3: packed FMUL2 / FADD2.
@@ -267,6 +286,15 @@ cudaError_t rt_launch_trace_rays(const float4 *sph, const uint32_t *skip, uint32
     if (n_rays == 0) return cudaSuccess;
     unsigned blocks = (unsigned)((n_rays + 127) / 128);
     trace_rays_kernel<<<blocks, 128, 0, stream>>>(sph, skip, n, n_rays, rays, hits);
+    return cudaGetLastError();
+}
+
+cudaError_t rt_launch_pack_rgb(const uint8_t *rgba, uint8_t *rgb, size_t n_px, cudaStream_t stream) {
+    if (n_px == 0) return cudaSuccess;
+    const size_t quads = n_px / 4;
+    const unsigned blocks = (unsigned)((quads + 255) / 256);
+    pack_rgb_kernel<<<blocks ? blocks : 1, 256, 0, stream>>>(reinterpret_cast<const uint32_t *>(rgba),
+                                                              reinterpret_cast<uint32_t *>(rgb), quads, n_px);
     return cudaGetLastError();
 }
 

@@ -213,10 +213,11 @@ struct Renderer {
     }
 
     // A sweep of frames on one GPU (extension): the device-to-host copy of frame f overlaps the
-    // render of frame f+1 (rt_render_sweep).  `sink(f, buffer)` is called once per frame, in order.
+    // render of frame f+1 (rt_render_sweep).  `sink(f, bytes, len)` is called once per frame, in order;
+    // with rgb = true the frames arrive as RGB8 (the body of the P6 file, alpha already dropped).
     template <class Sink>
     static void render_sweep(const RenderOptions &o, const Scene &scene, const std::vector<rt_camera> &cameras,
-                             Sink &&sink, rt_stats *stats = nullptr) {
+                             Sink &&sink, rt_stats *stats = nullptr, bool rgb = false) {
         struct Ctx {
             Sink *sink;
             const RenderOptions *o;
@@ -225,8 +226,8 @@ struct Renderer {
             Ctx *c = static_cast<Ctx *>(user);
             (*c->sink)(frame, rgba, len);
         };
-        rt_check(rt_render_sweep(scene.replicas()[0], cameras.data(), (uint32_t)cameras.size(), o.width, o.height,
-                                 o.samples_per_pixel, trampoline, &ctx, stats),
+        rt_check((rgb ? rt_render_sweep_rgb : rt_render_sweep)(scene.replicas()[0], cameras.data(), (uint32_t)cameras.size(),
+                                                               o.width, o.height, o.samples_per_pixel, trampoline, &ctx, stats),
                  "Renderer::render_sweep");
     }
 };

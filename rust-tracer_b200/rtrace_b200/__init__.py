@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "rt_last_error", "rt_version", "rt_device_count", "rt_set_device", "rt_set_variant",
     "rt_scene_create", "rt_scene_create_default", "rt_scene_create_from_nodes", "rt_scene_destroy",
     "rt_scene_counts", "rt_scene_export_nodes", "rt_flatten_pyramid_host", "rt_scene_light", "rt_scene_eye",
-    "rt_scene_device", "rt_render_region", "rt_render_rows", "rt_render_frame", "rt_render_sweep",
+    "rt_scene_device", "rt_render_region", "rt_render_rows", "rt_render_frame", "rt_render_sweep", "rt_render_sweep_rgb",
     "rt_render_frame_multi",
     "rt_count_rays", "rt_trace_rays", "rt_measure_fp32_peak", "rt_microbench_fp32", "rt_selftest_math", "rt_host_alloc", "rt_host_free", "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_memcpy",
 ]
@@ -79,6 +79,7 @@ def lib():
                                  C.POINTER(Stats)]
     L.rt_render_frame.argtypes = [vp, C.POINTER(Camera), u32, u32, u32, u8p, C.c_size_t, C.POINTER(Stats)]
     L.rt_render_sweep.argtypes = [vp, C.POINTER(Camera), u32, u32, u32, u32, FRAME_CALLBACK, vp, C.POINTER(Stats)]
+    L.rt_render_sweep_rgb.argtypes = L.rt_render_sweep.argtypes
     L.rt_render_frame_multi.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(Camera), u32, u32, u32, u8p, C.c_size_t,
                                         C.POINTER(Stats)]
     L.rt_count_rays.argtypes = [vp, C.POINTER(Camera), u32, u32, u32, u32, u32, u32, u64p, u64p]
@@ -300,8 +301,9 @@ class Renderer:
         return (out, st) if want_stats else out
 
     @staticmethod
-    def render_sweep(options, scene, n_frames, cameras=None, on_frame=None):
-        """n_frames frames, copy of frame f overlapping the render of f+1; on_frame(f, array) per frame."""
+    def render_sweep(options, scene, n_frames, cameras=None, on_frame=None, rgb=False):
+        """n_frames frames, copy of frame f overlapping the render of f+1; on_frame(f, array) per frame.
+        rgb=True delivers (h, w, 3) frames packed on the device (the P6 file body)."""
         w, h, spp = options.width, options.height, options.samples_per_pixel
         cams = None
         if cameras is not None:
@@ -309,11 +311,12 @@ class Renderer:
 
         def _cb(user, frame, ptr, nbytes):
             if on_frame is not None:
-                on_frame(int(frame), np.ctypeslib.as_array(ptr, shape=(h, w, 4)))
+                on_frame(int(frame), np.ctypeslib.as_array(ptr, shape=(h, w, 3 if rgb else 4)))
 
         cb = FRAME_CALLBACK(_cb)
         st = Stats()
-        _check(lib().rt_render_sweep(scene.handle, cams, n_frames, w, h, spp, cb, None, C.byref(st)))
+        fn = lib().rt_render_sweep_rgb if rgb else lib().rt_render_sweep
+        _check(fn(scene.handle, cams, n_frames, w, h, spp, cb, None, C.byref(st)))
         return st
 
     @staticmethod

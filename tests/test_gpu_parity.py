@@ -188,6 +188,14 @@ def test_sweep_delivers_every_frame_in_order(rt, oracle, gpu_scene8, oracle_scen
             getattr(oc, k)[:] = getattr(cams[f], k)[:]
         ref, _ = oracle_scene8.render(w, h, spp, camera=oc)
         assert_same(got[f], ref, "sweep frame %d" % f)
+    # RGB sweep: the same frames without the alpha byte (odd pixel count exercises the tail)
+    rgbs = {}
+    rt.Renderer.render_sweep(rt.RenderOptions(w, h, spp), gpu_scene8, n, cameras=cams, rgb=True,
+                             on_frame=lambda f, a: rgbs.__setitem__(f, a.copy()))
+    assert all(np.array_equal(rgbs[f], got[f][:, :, :3]) for f in range(n))
+    odd = {}
+    rt.Renderer.render_sweep(rt.RenderOptions(33, 7, 1), gpu_scene8, 1, rgb=True, on_frame=lambda f, a: odd.__setitem__(f, a.copy()))
+    assert np.array_equal(odd[0], oracle_scene8.render(33, 7, 1)[0][:, :, :3])
     # reference camera when no cameras are given
     got.clear()
     rt.Renderer.render_sweep(rt.RenderOptions(w, h, spp), gpu_scene8, 3, on_frame=lambda f, a: got.__setitem__(f, a.copy()))
