@@ -218,8 +218,8 @@ def main():
         max_rows = partition.band_capacity(height, world)
     else:
         my_rows, max_rows, row_start, row_stride = height, height, 0, 1
-    fb = torch.zeros((max_rows, width, 4), dtype=torch.uint8, device="cuda")
-    gathered = [torch.zeros_like(fb) for _ in range(world)] if (bands and rank == 0) else None
+    fb = torch.zeros((max_rows + 16, width, 4), dtype=torch.uint8, device="cuda")   # + one row block (blocked partition)
+    gathered = [torch.zeros_like(fb[:max_rows]) for _ in range(world)] if (bands and rank == 0) else None
     frame_box = [None]
     peer = bands and args.gather == "peer"
     peer_ptr, peer_pitch = None, 0
@@ -232,26 +232,32 @@ def main():
         dist.broadcast(handle, src=0)
         if rank != 0:
             frame_base = rt.ipc_open(bytes(handle.cpu().numpy().tobytes()))
-        peer_ptr, peer_pitch = frame_base + rank * width * 4, world * width * 4
+        # blocks of 16 consecutive rows per rank (whole cull tiles stay contiguous in the image)
+        row_start, row_stride, row_block, my_rows = partition.block_band_spec(height, rank, world, 16)
 
     # kernels launched per step (the PHASED variant is four launches per frame)
-    _, st0 = rt.Renderer.render_rows(opts, scene, row_start=row_start, row_stride=row_stride, row_count=my_rows,
+    _, st0 = rt.Renderer.render_rows(opts, scene, row_start=0, row_stride=1, row_count=min(my_rows, height),
                                      out_ptr=fb.data_ptr(), stream=stream.cuda_stream, want_stats=True)
     launches_per_step = int(st0.kernel_launches)
     # rays of this rank's share of a step, counted on the device the way the reference's work is counted
-    primary, shadow = scene.count_rays(width, height, spp, row_start, row_stride, my_rows)
+    if peer:   # blocked partition: count whole-frame rays once; each rank gets its share by pixel count
+        primary_all, shadow_all = scene.count_rays(width, height, spp)
+        primary = width * my_rows * spp * spp
+        shadow = int(round(shadow_all * my_rows / height))
+    else:
+        primary, shadow = scene.count_rays(width, height, spp, row_start, row_stride, my_rows)
     rays_rank = primary + shadow
     flush = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def step():
         if peer:   # the traversal kernels' framebuffer stores ARE the gather (NVLink peer writes)
-            rt.Renderer.render_rows(opts, scene, row_start=row_start, row_stride=row_stride, row_count=my_rows,
-                                    out_ptr=peer_ptr, pitch=peer_pitch, stream=stream.cuda_stream)
+            rt.Renderer.render_row_blocks(opts, scene, row_start, row_stride, row_block, my_rows, frame_base,
+                                          pitch=width * 4, absolute_rows=True, stream=stream.cuda_stream)
             return
         rt.Renderer.render_rows(opts, scene, row_start=row_start, row_stride=row_stride, row_count=my_rows,
                                 out_ptr=fb.data_ptr(), stream=stream.cuda_stream)
         if bands:
-            dist.gather(fb, gathered, dst=0)
+            dist.gather(fb[:max_rows], gathered, dst=0)
             if rank == 0:   # de-interleave: row r*world + g  <-  band g row r
                 frame_box[0] = partition.deinterleave(gathered, height)
 
@@ -303,12 +309,13 @@ def main():
     def on_frame(f, arr):
         seen.append(int(arr[0, 0, 0]))   # touch the host copy of every frame
 
-    pinned = rt.PinnedBuffer(max(my_rows, 1) * width * 4) if bands else None
+    e_start, e_stride, e_rows = partition.band_spec(height, rank, world) if bands else (0, 1, height)
+    pinned = rt.PinnedBuffer(max(e_rows, 1) * width * 4) if bands else None
 
     def e2e_run(n):
         if bands:
             for _ in range(n):
-                rt.Renderer.render_rows(opts, scene, row_start=row_start, row_stride=row_stride, row_count=my_rows,
+                rt.Renderer.render_rows(opts, scene, row_start=e_start, row_stride=e_stride, row_count=e_rows,
                                         out_ptr=pinned.ptr)
         else:
             rt.Renderer.render_sweep(opts, scene, n, on_frame=on_frame, rgb=True)
@@ -366,7 +373,7 @@ def main():
                 "workload": "%s: pyramid level %d (%d spheres) at %dx%d, %d spp" % (
                     args.workload, level, (4 ** level - 1) // 3, width, height, spp * spp),
                 "partition": (("interleaved row bands; kernels store into rank 0's frame through IPC peer memory (NVLink)"
-                               if peer else "interleaved row bands + NCCL gather to rank 0") if bands else
+                               " in blocks of 16 rows" if peer else "interleaved row bands + NCCL gather to rank 0") if bands else
                               "one whole frame per rank per step (frame-sharded sweep), no collective"),
                 "l2": "not flushed" if flush is None else "flushed between steps (256 MiB memset, outside the timed events)",
                 "rays_per_frame": {"primary": primary * (world if bands else 1), "shadow": None if bands else shadow},

@@ -134,6 +134,19 @@ int rt_render_rows(const rt_scene *s, const rt_camera *camera,
                    uint8_t *rgba_out, size_t pitch_bytes, uint8_t *kinds_out,
                    void *stream, rt_stats *stats);
 
+/* rt_render_rows with the rows taken in BLOCKS: local row j is image row
+ * row_start + (j / row_block) * row_stride + j % row_block (row_block a power of two,
+ * row_stride >= row_block).  Rank r of N renders row_start = r*B, row_stride = N*B: whole tiles
+ * stay contiguous in the image, so the tile culls stay as tight as on one GPU.  With
+ * absolute_rows != 0, rgba_out is the base of a WHOLE device frame (possibly a peer GPU's, e.g. rank
+ * 0's through rt_ipc_open) and row j is stored at rgba_out + image_row * pitch: the kernels' stores are
+ * the gather. */
+int rt_render_row_blocks(const rt_scene *s, const rt_camera *camera,
+                         uint32_t width, uint32_t height, uint32_t spp,
+                         uint32_t row_start, uint32_t row_stride, uint32_t row_block, uint32_t row_count,
+                         uint8_t *rgba_out, size_t pitch_bytes, int absolute_rows,
+                         void *stream, rt_stats *stats);
+
 /* Whole frame to a host or device buffer of width*height*4 bytes on the scene's GPU. */
 int rt_render_frame(const rt_scene *s, const rt_camera *camera,
                     uint32_t width, uint32_t height, uint32_t spp,

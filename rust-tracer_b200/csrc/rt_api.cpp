@@ -6,6 +6,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -65,6 +66,9 @@ struct rt_scene {
 namespace {
 
 thread_local char g_err[512] = "";
+// rt_render_row_blocks sets these around its call into render_rows_impl (0 / false otherwise)
+thread_local uint32_t g_row_block_shift = 0;
+thread_local bool g_out_abs = false;
 thread_local int g_variant = RT_VARIANT_AUTO;
 
 int fail(int code, const char *fmt, ...) {
@@ -167,6 +171,8 @@ void fill_params(const rt_scene *s, const rt_camera *cam, uint32_t w, uint32_t h
     p.row_start = row_start;
     p.row_stride = row_stride;
     p.row_count = row_count;
+    p.row_block_shift = g_row_block_shift;
+    p.out_abs = g_out_abs ? 1 : 0;
 }
 
 int check_frame_args(const rt_scene *s, uint32_t w, uint32_t h, uint32_t spp, uint32_t row_start, uint32_t row_stride,
@@ -176,8 +182,12 @@ int check_frame_args(const rt_scene *s, uint32_t w, uint32_t h, uint32_t spp, ui
     if (w == 0 || h == 0 || w > 65535u || h > 65535u || spp > 65535u)
         return fail(RT_ERR_INVALID, "width/height must be in 1..65535 and samples-per-pixel in 0..65535 (got %u x %u, spp %u)", w, h, spp);
     if (row_stride == 0) return fail(RT_ERR_INVALID, "row_stride must be >= 1");
-    if (row_count > 0 && (uint64_t)row_start + (uint64_t)(row_count - 1) * row_stride >= h)
-        return fail(RT_ERR_INVALID, "rows %u + k*%u (k < %u) leave the %u-row image", row_start, row_stride, row_count, h);
+    if (row_count > 0) {
+        const uint32_t j = row_count - 1, bs = g_row_block_shift;
+        const uint64_t last = (uint64_t)row_start + (uint64_t)(j >> bs) * row_stride + (j & ((1u << bs) - 1u));
+        if (last >= h) return fail(RT_ERR_INVALID, "rows starting at %u (stride %u, blocks of %u, %u rows) leave the %u-row image", row_start, row_stride, 1u << bs, row_count, h);
+        if (bs && row_stride < (1u << bs)) return fail(RT_ERR_INVALID, "row_stride %u is smaller than the row block %u", row_stride, 1u << bs);
+    }
     return RT_OK;
 }
 
@@ -492,6 +502,7 @@ static int render_rows_impl(rt_scene *s, const rt_camera *camera, uint32_t width
     const bool kinds_on_device = kinds_out && is_device_ptr(kinds_out, &kinds_dev);
     const size_t kinds_bytes = (size_t)width * row_count * spp * spp;
 
+    if (g_out_abs && !out_on_device) return fail(RT_ERR_INVALID, "absolute row addressing needs a device (or peer) frame buffer");
     const bool need_lock = !out_on_device || (kinds_out && !kinds_on_device) || counting || stats;
     std::unique_lock<std::mutex> lock(s->mu, std::defer_lock);
     if (need_lock) lock.lock();
@@ -571,6 +582,21 @@ int rt_render_rows(const rt_scene *s, const rt_camera *camera, uint32_t width, u
                    uint8_t *kinds_out, void *stream, rt_stats *stats) {
     return render_rows_impl(const_cast<rt_scene *>(s), camera, width, height, spp, row_start, row_stride, row_count,
                             rgba_out, pitch_bytes, kinds_out, (cudaStream_t)stream, stats, nullptr, nullptr);
+}
+
+int rt_render_row_blocks(const rt_scene *s, const rt_camera *camera, uint32_t width, uint32_t height, uint32_t spp,
+                         uint32_t row_start, uint32_t row_stride, uint32_t row_block, uint32_t row_count, uint8_t *rgba_out,
+                         size_t pitch_bytes, int absolute_rows, void *stream, rt_stats *stats) {
+    if (row_block == 0 || (row_block & (row_block - 1u)) || row_block > 32768u) return fail(RT_ERR_INVALID, "row_block must be a power of two (got %u)", row_block);
+    uint32_t shift = 0;
+    while ((1u << shift) < row_block) shift++;
+    g_row_block_shift = shift;
+    g_out_abs = absolute_rows != 0;
+    int rc = render_rows_impl(const_cast<rt_scene *>(s), camera, width, height, spp, row_start, row_stride, row_count,
+                              rgba_out, pitch_bytes, nullptr, (cudaStream_t)stream, stats, nullptr, nullptr);
+    g_row_block_shift = 0;
+    g_out_abs = false;
+    return rc;
 }
 
 int rt_render_region(const rt_scene *s, uint16_t width, uint16_t height, uint16_t spp, uint16_t l, uint16_t b,
@@ -729,15 +755,26 @@ int rt_render_frame_multi(rt_scene *const *scenes, int ngpu, const rt_camera *ca
                 peer = true;
             }
         }
-        const uint32_t rows = (height > (uint32_t)g) ? (height - g + ngpu - 1) / ngpu : 0;
-        if (rows == 0) continue;
         rt::RenderParams p;
-        fill_params(s, camera, width, height, spp, (uint32_t)g, (uint32_t)ngpu, rows, p);
+        uint32_t rows;
         if (peer) {
-            // rows g, g+G, ... written in place: GPU g's stores land in GPU 0's frame over NVLink
-            p.out = frame + row_bytes * g;
-            p.pitch = row_bytes * ngpu;
+            // GPU g renders blocks of 16 consecutive rows, G blocks apart (whole cull tiles stay contiguous
+            // in the image), and stores them at their image rows in GPU 0's frame: over NVLink for g > 0
+            const uint32_t B = 16, first = (uint32_t)g * B, stride = (uint32_t)ngpu * B;
+            rows = 0;
+            for (uint64_t y0 = first; y0 < height; y0 += stride) rows += (uint32_t)std::min<uint64_t>(B, height - y0);
+            if (rows == 0) continue;
+            g_row_block_shift = 4;
+            g_out_abs = true;
+            fill_params(s, camera, width, height, spp, first, stride, rows, p);
+            g_row_block_shift = 0;
+            g_out_abs = false;
+            p.out = frame;
+            p.pitch = row_bytes;
         } else {
+            rows = (height > (uint32_t)g) ? (height - g + ngpu - 1) / ngpu : 0;
+            if (rows == 0) continue;
+            fill_params(s, camera, width, height, spp, (uint32_t)g, (uint32_t)ngpu, rows, p);
             int rc = ensure(&s->d_fb, &s->d_fb_cap, row_bytes * rows);
             if (rc != RT_OK) return rc;
             p.out = s->d_fb;
@@ -751,6 +788,7 @@ int rt_render_frame_multi(rt_scene *const *scenes, int ngpu, const rt_camera *ca
         if (stats) CUDA_TRY(cudaEventRecord(s->ev1, s->own_stream));
         if (!peer)  // no peer access: strided copy, the pitch de-interleaves the band into the frame
             CUDA_TRY(cudaMemcpy2DAsync(frame + row_bytes * g, row_bytes * ngpu, s->d_fb, row_bytes, row_bytes, rows, cudaMemcpyDefault, s->own_stream));
+        (void)rows;
     }
     double kmax = 0.0;
     for (int g = ngpu - 1; g >= 0; g--) {

@@ -91,6 +91,8 @@ struct RenderParams {
     int has_basis;
     uint32_t width, height, spp;
     uint32_t row_start, row_stride, row_count;  // image rows rendered by this launch
+    uint32_t row_block_shift;                   // rows come in blocks of 2^shift consecutive image rows
+    int out_abs;                                // rows are stored at their IMAGE row (out = base of a whole frame)
     uint8_t *out;                               // RGBA8, row j at out + j*pitch
     size_t pitch;
     // PHASED variant scratch (L2-resident intermediates between the four launches)
@@ -102,6 +104,14 @@ struct RenderParams {
     uint8_t *kinds;                    // optional per-sample classification
     unsigned long long *ray_counters;  // optional {primary_hits, shadow_rays}
 };
+
+// Local row j of this launch -> image row: blocks of 2^shift consecutive rows, row_stride apart
+// (shift 0: the plain interleave row_start + j * row_stride).
+RT_DEV uint32_t image_row(const RenderParams &p, uint32_t j) {
+    return p.row_start + (j >> p.row_block_shift) * p.row_stride + (j & ((1u << p.row_block_shift) - 1u));
+}
+// Row of the output buffer that local row j is stored in.
+RT_DEV uint32_t out_row(const RenderParams &p, uint32_t j) { return p.out_abs ? image_row(p, j) : j; }
 
 // Shading constants, render.rs:172-186 (single f32 operations, as rustc const-evaluates them).
 struct ShadeConsts {

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) render_kernel(const RenderParam
     const uint32_t j = blockIdx.y * (TILE_H * WARPS_Y) + (warp / WARPS_X) * TILE_H + (lane / TILE_W);
     const bool inside = x < p.width && j < p.row_count;
     if (VARIANT == RT_KERNEL_LANE && !inside) return;
-    const uint32_t y = p.row_start + j * p.row_stride;
+    const uint32_t y = image_row(p, j);
 
     const ShadeConsts K = shade_consts();
     const V3 eye = v3(p.eye[0], p.eye[1], p.eye[2]);
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) render_kernel(const RenderParam
         c = vmulf(c, recip);
         alpha = fmul(alpha, recip);
         uint32_t px = scale_u8(c.x) | (scale_u8(c.y) << 8) | (scale_u8(c.z) << 16) | (scale_u8(alpha) << 24);
-        *reinterpret_cast<uint32_t *>(p.out + (size_t)j * p.pitch + (size_t)x * 4) = px;
+        *reinterpret_cast<uint32_t *>(p.out + (size_t)out_row(p, j) * p.pitch + (size_t)x * 4) = px;
     }
     if (DIAG && p.ray_counters) {
         if (!inside) {

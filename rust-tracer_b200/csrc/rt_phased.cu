@@ -65,7 +65,7 @@ RT_DEV PrimaryBeam cull_tile_beam(const RenderParams &p, uint32_t ct_x, uint32_t
     const float frac = G::FRAC;
     const uint32_t x0 = ct_x * G::BW, j0 = ct_y * G::BH;
     const uint32_t xh = min(x0 + G::BW, p.width) - 1u, jh = min(j0 + G::BH, p.row_count) - 1u;
-    const float ya = (float)(p.row_start + j0 * p.row_stride), yb = (float)(p.row_start + jh * p.row_stride);
+    const float ya = (float)(image_row(p, j0)), yb = (float)(image_row(p, jh));
     return make_primary_beam(p, (float)x0, (float)xh + frac, fminf(ya, yb), fmaxf(ya, yb) + frac);
 }
 
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(32 * CW * CH, RT_PHASED_MINBLOCKS) phase_test_
             slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s / NS, x, j);
             uint32_t bi = NO_HIT;
             if (x < p.width && j < p.row_count) {
-                const V3 d = slot_dir<SPP>(p, x, p.row_start + j * p.row_stride, s % NS);
+                const V3 d = slot_dir<SPP>(p, x, image_row(p, j), s % NS);
                 float hitd = RT_INF;
                 lane_traverse<false>(p.sph, p.skip, p.n_nodes, eye, d, hitd, bi);
                 if (hitd == RT_INF) bi = NO_HIT;
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(32 * CW * CH, RT_PHASED_MINBLOCKS) phase_test_
         {
             const float frac = (float)(SPP - 1) / (float)SPP;
             const uint32_t xh = min(bx + PXW, p.width) - 1u, jh = min(bj + PXH, p.row_count) - 1u;
-            const float ya = (float)(p.row_start + bj * p.row_stride), yb = (float)(p.row_start + jh * p.row_stride);
+            const float ya = (float)(image_row(p, bj)), yb = (float)(image_row(p, jh));
             lb = make_primary_beam(p, (float)bx, (float)xh + frac, fminf(ya, yb), fmaxf(ya, yb) + frac);
         }
         // the warp's pixel tile: between the cull tile's cone and the lane's
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(32 * CW * CH, RT_PHASED_MINBLOCKS) phase_test_
         {
             const float frac = (float)(SPP - 1) / (float)SPP;
             const uint32_t xh = min(tile_x0 + G::TW, p.width) - 1u, jh = min(tile_j0 + G::TH, p.row_count) - 1u;
-            const float ya = (float)(p.row_start + tile_j0 * p.row_stride), yb = (float)(p.row_start + jh * p.row_stride);
+            const float ya = (float)(image_row(p, tile_j0)), yb = (float)(image_row(p, jh));
             wb = make_primary_beam(p, (float)tile_x0, (float)xh + frac, fminf(ya, yb), fmaxf(ya, yb) + frac);
         }
         // candidates c0..c1 (at most 32) of a chunk -> bit mask of those this LANE's block can see.
@@ -216,8 +216,8 @@ __global__ void __launch_bounds__(32 * CW * CH, RT_PHASED_MINBLOCKS) phase_test_
             uint32_t x0, j0, x1, j1;
             slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s0 / NS, x0, j0);
             slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s1 / NS, x1, j1);
-            const V3x2 d = slot_dir2<SPP>(one, p, x0, p.row_start + j0 * p.row_stride, s0 % NS, x1,
-                                          p.row_start + j1 * p.row_stride, s1 % NS);
+            const V3x2 d = slot_dir2<SPP>(one, p, x0, image_row(p, j0), s0 % NS, x1,
+                                          image_row(p, j1), s1 % NS);
             F2 bd = f2s(RT_INF);
             uint32_t bi0 = NO_HIT, bi1 = NO_HIT;
             auto test = [&](const uint4 u0, const uint4 u1, const uint4 u2) {
@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(32 * CW * CH, RT_PHASED_MINBLOCKS) phase_shade
                 uint32_t x, j;
                 slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, pi, x, j);
                 if (x < p.width && j < p.row_count) {
-                    *reinterpret_cast<uint32_t *>(p.out + (size_t)j * p.pitch + (size_t)x * 4) = px;
+                    *reinterpret_cast<uint32_t *>(p.out + (size_t)out_row(p, j) * p.pitch + (size_t)x * 4) = px;
                     if (DIAG && p.kinds)
                         for (int smp = 0; smp < NS; smp++) p.kinds[((size_t)j * p.width + x) * NS + smp] = K_BACKGROUND;
                 }
@@ -398,8 +398,8 @@ __global__ void __launch_bounds__(32 * CW * CH, RT_PHASED_MINBLOCKS) phase_shade
             uint32_t x0, j0, x1, j1;
             slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s0 / NS, x0, j0);
             slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s1 / NS, x1, j1);
-            const V3x2 d = slot_dir2<SPP>(one, p, x0, p.row_start + j0 * p.row_stride, s0 % NS, x1,
-                                          p.row_start + j1 * p.row_stride, s1 % NS);
+            const V3x2 d = slot_dir2<SPP>(one, p, x0, image_row(p, j0), s0 % NS, x1,
+                                          image_row(p, j1), s1 % NS);
             const uint32_t wi0 = winner[s0 * 32 + lane], wi1 = winner[s1 * 32 + lane];
             const bool hit0 = wi0 != NO_HIT, hit1 = wi1 != NO_HIT;
             const float4 w0 = __ldg(&p.sph[hit0 ? wi0 : 0u]), w1 = __ldg(&p.sph[hit1 ? wi1 : 0u]);
@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(32 * CW * CH, RT_PHASED_MINBLOCKS) phase_shade
                         const float al = fmul(alpha, recip);
                         const uint32_t px = scale_u8_fast(q.x) | (scale_u8_fast(q.y) << 8) |
                                             (scale_u8_fast(q.z) << 16) | (scale_u8_fast(al) << 24);
-                        *reinterpret_cast<uint32_t *>(p.out + (size_t)j * p.pitch + (size_t)x * 4) = px;
+                        *reinterpret_cast<uint32_t *>(p.out + (size_t)out_row(p, j) * p.pitch + (size_t)x * 4) = px;
                     }
                 }
             }

@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "rt_last_error", "rt_version", "rt_device_count", "rt_set_device", "rt_set_variant",
     "rt_scene_create", "rt_scene_create_default", "rt_scene_create_from_nodes", "rt_scene_destroy",
     "rt_scene_counts", "rt_scene_export_nodes", "rt_flatten_pyramid_host", "rt_scene_light", "rt_scene_eye",
-    "rt_scene_device", "rt_render_region", "rt_render_rows", "rt_render_frame", "rt_render_sweep", "rt_render_sweep_rgb",
+    "rt_scene_device", "rt_render_region", "rt_render_rows", "rt_render_row_blocks", "rt_render_frame", "rt_render_sweep", "rt_render_sweep_rgb",
     "rt_render_frame_multi",
     "rt_count_rays", "rt_trace_rays", "rt_measure_fp32_peak", "rt_microbench_fp32", "rt_selftest_math", "rt_host_alloc", "rt_host_free", "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_memcpy",
 ]
@@ -77,6 +77,8 @@ def lib():
     L.rt_render_region.argtypes = [vp, u16, u16, u16, u16, u16, u16, u16, u8p, C.c_size_t]
     L.rt_render_rows.argtypes = [vp, C.POINTER(Camera), u32, u32, u32, u32, u32, u32, u8p, C.c_size_t, u8p, vp,
                                  C.POINTER(Stats)]
+    L.rt_render_row_blocks.argtypes = [vp, C.POINTER(Camera), u32, u32, u32, u32, u32, u32, u32, u8p, C.c_size_t,
+                                       C.c_int, vp, C.POINTER(Stats)]
     L.rt_render_frame.argtypes = [vp, C.POINTER(Camera), u32, u32, u32, u8p, C.c_size_t, C.POINTER(Stats)]
     L.rt_render_sweep.argtypes = [vp, C.POINTER(Camera), u32, u32, u32, u32, FRAME_CALLBACK, vp, C.POINTER(Stats)]
     L.rt_render_sweep_rgb.argtypes = L.rt_render_sweep.argtypes
@@ -286,6 +288,17 @@ class Renderer:
         if want_stats:
             res.append(st)
         return res[0] if len(res) == 1 else tuple(res)
+
+    @staticmethod
+    def render_row_blocks(options, scene, row_start, row_stride, row_block, row_count, out_ptr, pitch=0,
+                          absolute_rows=False, camera=None, stream=None, want_stats=False):
+        """Rows in blocks of `row_block` consecutive image rows, `row_stride` apart (device output only)."""
+        w, h, spp = options.width, options.height, options.samples_per_pixel
+        st = Stats() if want_stats else None
+        _check(lib().rt_render_row_blocks(scene.handle, C.byref(camera) if camera is not None else None, w, h, spp,
+                                          row_start, row_stride, row_block, row_count, out_ptr, pitch,
+                                          1 if absolute_rows else 0, stream, C.byref(st) if st is not None else None))
+        return st
 
     @staticmethod
     def render(options, scene, camera=None, out=None, out_ptr=None, want_stats=False):

@@ -34,3 +34,17 @@ def deinterleave(bands, height):
         import numpy as np
         frame = np.stack(list(bands), axis=1).reshape((cap * world,) + tuple(bands[0].shape[1:]))
     return frame[:height]
+
+
+def block_band_spec(height, rank, world, block=16):
+    """(row_start, row_stride, row_block, row_count) for Renderer.render_row_blocks: rank `rank` renders
+    blocks of `block` consecutive rows, `world` blocks apart, so whole tiles stay contiguous in the image."""
+    start, stride = rank * block, world * block
+    count = sum(min(block, height - y0) for y0 in range(start, height, stride))
+    return start, stride, block, count
+
+
+def block_band_rows(height, rank, world, block=16):
+    """The image rows of that band, in local-row order."""
+    start, stride = rank * block, world * block
+    return [y for y0 in range(start, height, stride) for y in range(y0, min(y0 + block, height))]

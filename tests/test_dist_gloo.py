@@ -75,3 +75,12 @@ def test_partition_arithmetic():
                 for k in range(rows[r]):
                     bands[r][k] = r + k * g
             assert (partition.deinterleave(bands, h)[:, 0] == np.arange(h)).all()
+            # blocked partition: every row exactly once, counts agree
+            for block in (4, 16):
+                allrows = []
+                for r in range(g):
+                    start, stride, blk, count = partition.block_band_spec(h, r, g, block)
+                    rows_r = partition.block_band_rows(h, r, g, block)
+                    assert len(rows_r) == count and blk == block and (not rows_r or rows_r[0] == start)
+                    allrows += rows_r
+                assert sorted(allrows) == list(range(h))

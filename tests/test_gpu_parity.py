@@ -289,3 +289,33 @@ def test_other_scenes_at_high_resolution(rt, oracle):
             assert_same(rt.Renderer.render(rt.RenderOptions(w, h, spp), gs), ref, "variant %d" % v)
     finally:
         rt.set_variant(rt.VARIANT_AUTO)
+
+
+def test_blocked_rows_and_absolute_addressing(rt, oracle_scene8, gpu_scene8):
+    """rt_render_row_blocks: rank r of N renders blocks of B rows, N blocks apart, and stores each row
+    at its image row of a whole frame -- the ranks' stores together are the gathered frame."""
+    torch = pytest.importorskip("torch")
+    from rtrace_b200 import partition
+    w, h, spp = 200, 150, 2   # 150 is not a multiple of the block: the last block is partial
+    ref, _ = oracle_scene8.render(w, h, spp)
+    o = rt.RenderOptions(w, h, spp)
+    for world, block in ((3, 16), (2, 8), (8, 16)):
+        frame = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+        seen = []
+        for rank in range(world):
+            start, stride, blk, count = partition.block_band_spec(h, rank, world, block)
+            seen += partition.block_band_rows(h, rank, world, block)
+            if count:
+                rt.Renderer.render_row_blocks(o, gpu_scene8, start, stride, blk, count, frame.data_ptr(), pitch=w * 4,
+                                              absolute_rows=True, stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert sorted(seen) == list(range(h))
+        assert np.array_equal(frame.cpu().numpy(), ref), "world %d block %d" % (world, block)
+    # dense band (absolute_rows off): local row j is block row j
+    start, stride, blk, count = partition.block_band_spec(h, 1, 3, 16)
+    band = torch.zeros((count, w, 4), dtype=torch.uint8, device="cuda")
+    rt.Renderer.render_row_blocks(o, gpu_scene8, start, stride, blk, count, band.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(band.cpu().numpy(), ref[partition.block_band_rows(h, 1, 3, 16)])
+    with pytest.raises(rt.RtError):
+        rt.Renderer.render_row_blocks(o, gpu_scene8, 0, 48, 12, 10, band.data_ptr())   # block not a power of two
