@@ -206,6 +206,11 @@ int rt_microbench_fp32(int device, int mode, double *tflops);
  * inputs; all six mismatch counters must be 0. */
 int rt_selftest_math(uint32_t n, uint32_t seed, uint64_t mismatches[6]);
 
+/* Diagnostics: candidate counts per cull tile of the scene's most recent PHASED frame
+ * (counts[2t] = primary, counts[2t+1] = shadow candidates, 0xffffffff = tile rendered by the
+ * per-lane walk); *n_tiles = number of tiles, counts may be NULL to query it. */
+int rt_debug_phased_tiles(const rt_scene *s, uint32_t cap_tiles, uint32_t *n_tiles, uint32_t *counts);
+
 /* Device memory on the current device, and CUDA IPC handles for it: how the ranks of a
  * multi-process job (one process per GPU) hand rank 0's frame to the others, which then
  * pass `frame + rank*width*4` with pitch `world*width*4` to rt_render_rows -- their kernels

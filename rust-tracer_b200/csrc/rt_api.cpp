@@ -157,6 +157,23 @@ void fill_params(const rt_scene *s, const rt_camera *cam, uint32_t w, uint32_t h
         p.eye[k] = eye[k];
         p.light[k] = s->flat.light[k];
     }
+    {   // orthonormal pair perpendicular to the light: the plane the shadow pre-filter projects onto
+        const double lx = p.light[0], ly = p.light[1], lz = p.light[2];
+        const double ln = sqrt(lx * lx + ly * ly + lz * lz);
+        if (ln > 0.0) {
+            const double l[3] = {lx / ln, ly / ln, lz / ln};
+            int m = 0;  // axis least aligned with the light
+            if (fabs(l[1]) < fabs(l[m])) m = 1;
+            if (fabs(l[2]) < fabs(l[m])) m = 2;
+            double a[3] = {0.0, 0.0, 0.0};
+            a[m] = 1.0;
+            double e1[3] = {l[1] * a[2] - l[2] * a[1], l[2] * a[0] - l[0] * a[2], l[0] * a[1] - l[1] * a[0]};
+            const double n1 = sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
+            for (int k = 0; k < 3; k++) e1[k] /= n1;
+            const double e2[3] = {l[1] * e1[2] - l[2] * e1[1], l[2] * e1[0] - l[0] * e1[2], l[0] * e1[1] - l[1] * e1[0]};
+            for (int k = 0; k < 3; k++) p.lframe[k] = (float)e1[k], p.lframe[3 + k] = (float)e2[k];
+        }
+    }
     if (cam) {
         p.has_basis = 1;
         for (int k = 0; k < 3; k++) {
@@ -896,6 +913,39 @@ int rt_measure_fp32_peak(int device, double *tflops, double *sm_clock_mhz) {
         CUDA_TRY(cudaGetDeviceProperties(&prop, device));
         // effective clock implied by the measured rate: 128 FFMA lanes per SM per cycle
         *sm_clock_mhz = *tflops * 1e12 / (2.0 * 128.0 * prop.multiProcessorCount) / 1e6;
+    }
+    return RT_OK;
+}
+
+// Diagnostic: candidate counts per cull tile of the most recent PHASED frame of this scene
+// (walks the chunk chains on the host).  counts[2*t] = primary, counts[2*t+1] = shadow candidates;
+// 0xffffffff = tile handled by the per-lane walk.  Returns the number of tiles through *n_tiles.
+int rt_debug_phased_tiles(const rt_scene *cs, uint32_t cap_tiles, uint32_t *n_tiles, uint32_t *counts) {
+    rt_scene *s = const_cast<rt_scene *>(cs);
+    if (!s || !n_tiles) return fail(RT_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(s->device);
+    CUDA_TRY(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lock(s->mu_phased);
+    if (s->phased.empty()) return fail(RT_ERR_INVALID, "no PHASED frame rendered yet");
+    rt_scene::Phased &ph = s->phased.begin()->second;
+    const uint32_t nt = (uint32_t)(ph.hdr_cap / sizeof(uint4));
+    *n_tiles = nt;
+    if (!counts) return RT_OK;
+    uint32_t used = 0;
+    CUDA_TRY(cudaMemcpy(&used, ph.pool_count, sizeof(used), cudaMemcpyDeviceToHost));
+    used = std::min(used, ph.pool_units);
+    std::vector<uint4> hdr(nt), pool(used);
+    CUDA_TRY(cudaMemcpy(hdr.data(), ph.hdr, (size_t)nt * sizeof(uint4), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(pool.data(), ph.pool, (size_t)used * sizeof(uint4), cudaMemcpyDeviceToHost));
+    for (uint32_t t = 0; t < nt && t < cap_tiles; t++) {
+        const uint32_t heads[2] = {hdr[t].x, hdr[t].y};
+        for (int k = 0; k < 2; k++) {
+            uint32_t n = 0, b = heads[k];
+            if (b == 0xfffffffeu) n = 0xffffffffu;
+            else
+                for (int guard_n = 0; b != 0xffffffffu && b < used && guard_n < 100000; guard_n++) n += pool[b].x, b = pool[b].y;
+            counts[2 * t + k] = n;
+        }
     }
     return RT_OK;
 }

@@ -87,6 +87,7 @@ struct RenderParams {
     uint32_t tile_stride;  // TILE variant: warp w renders tile (w * tile_stride) mod n_tiles
     float eye[3];
     float light[3];  // normalised directional light (render.rs:154-159)
+    float lframe[6];  // e1, e2: orthonormal pair perpendicular to the light (PHASED shadow pre-filter; not parity arithmetic)
     float basis[9];  // right, up, forward (camera extension)
     int has_basis;
     uint32_t width, height, spp;

@@ -69,34 +69,104 @@ RT_DEV PrimaryBeam cull_tile_beam(const RenderParams &p, uint32_t ct_x, uint32_t
     return make_primary_beam(p, (float)x0, (float)xh + frac, fminf(ya, yb), fmaxf(ya, yb) + frac);
 }
 
+// Conservative image-space bounds {x_lo, x_hi, y_lo, y_hi} (sample coordinates: pixel + sub-sample
+// offset, image rows) of the primary rays whose EXACT f32 test against a candidate can pass.
+// a = {v = c - eye, v.v}, rr = r*r.  A ray of raw direction (X, Y, Z) (render.rs:240-242) reaches the
+// sphere only if its projection on the camera's xz-plane passes within R of (qx, qz):
+// (qx Z - qz X)^2 <= R^2 (X^2 + Z^2), a quadratic in X/Z whose roots bound X; likewise Y.  R is the
+// radius inflated by the worst-case rounding of the discriminant (cull_radius) plus the f32 error of the
+// ray direction (< 5e-7 rad, at most 4e-6 at these distances).  Acceleration only: not parity arithmetic.
+RT_DEV float4 screen_box(const RenderParams &p, float4 a, float rr) {
+    float qx = a.x, qy = a.y, qz = a.z;
+    if (p.has_basis) {  // camera coordinates (orthonormal basis: checked by the host before this variant runs)
+        qx = fmaf(a.x, p.basis[0], fmaf(a.y, p.basis[1], a.z * p.basis[2]));
+        qy = fmaf(a.x, p.basis[3], fmaf(a.y, p.basis[4], a.z * p.basis[5]));
+        qz = fmaf(a.x, p.basis[6], fmaf(a.y, p.basis[7], a.z * p.basis[8]));
+    }
+    const float R = fmaf(asqrt(fmaf(EPS_DISC, a.w + rr, rr)), 1.001f, 1e-5f);
+    if (!(qz > 1.01f * R)) return make_float4(-RT_INF, RT_INF, -RT_INF, RT_INF);  // not strictly in front: no bound
+    const float A = fmaf(qz, qz, -R * R);
+    const float k = adiv((float)p.width, A);
+    const float cx = qx * qz * k, cy = qy * qz * k;
+    const float hx = R * asqrt(fmaf(qx, qx, A)) * k, hy = R * asqrt(fmaf(qy, qy, A)) * k;
+    const float sx = fmaf(hx, 1.0005f, fmaf(fabsf(cx), 1e-5f, 0.05f));
+    const float sy = fmaf(hy, 1.0005f, fmaf(fabsf(cy), 1e-5f, 0.05f));
+    const float hw = 0.5f * (float)p.width, hh = 0.5f * (float)p.height;
+    // x_res = X + W/2 ; y_res = H/2 - Y (render.rs:240-241)
+    return make_float4((cx - sx) + hw, (cx + sx) + hw, hh - (cy + sy), hh - (cy - sy));
+}
+RT_DEV bool box_overlaps(float4 box, float x0, float x1, float y0, float y1) {
+    return box.y >= x0 && box.x <= x1 && box.w >= y0 && box.z <= y1;
+}
+
+// Warp-wide float min / max through the integer REDUX instruction: the map below is monotonic
+// from float order (NaN-free inputs, +-inf included) to signed-int order and is its own inverse.
+RT_DEV int f2ord(float f) {
+    const int b = __float_as_int(f);
+    return b ^ ((b >> 31) & 0x7fffffff);
+}
+RT_DEV float ord2f(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
+RT_DEV float warp_min_f(float f) { return ord2f(__reduce_min_sync(FULLMASK, f2ord(f))); }
+RT_DEV float warp_max_f(float f) { return ord2f(__reduce_max_sync(FULLMASK, f2ord(f))); }
+
+static constexpr uint32_t PU = 4;  // 16-byte units per primary candidate record
+static constexpr uint32_t SU = 3;  // 16-byte units per shadow candidate record
+
 // Append the warp's candidate list to the pool as a chunk {count, next} + records, chained in
-// front of `head`.  Records are stored as broadcast PAIRS so that the packed f32x2 tests of K2 /
-// K4 (two rays per instruction) load their operands straight into register pairs:
-//   primary (3 units): {vx,vx,vy,vy} {vz,vz,-v.v,-v.v} {r*r,r*r,index,0}
-//   shadow  (2 units): {cx,cx,cy,cy} {cz,cz,r*r,r*r}
-template <int UNITS>
-RT_DEV uint32_t flush_chunk(const RenderParams &p, const CullShared &sm, int lane, uint32_t n, uint32_t head) {
-    if (n == 0 || head == OVERFLOWED) return head;
-    const uint32_t units = 1u + (uint32_t)UNITS * n;
+// front of `head`.  The exact-test operands are stored as broadcast PAIRS so that the packed f32x2
+// tests of K2 / K4 (two rays per instruction) load them straight into register pairs:
+//   primary (PU units): {vx,vx,vy,vy} {vz,vz,-v.v,-v.v} {r*r,r*r,index,0} {x_lo,x_hi,y_lo,y_hi}
+//   shadow  (SU units): {cx,cx,cy,cy} {cz,cz,r*r,r*r} {c.e1, c.e2, R^2, 0}
+// The last unit of each record is what the per-lane pre-filters read: the image-space box of the
+// rays that can hit (screen_box), and the candidate's disc in the plane perpendicular to the light.
+RT_DEV uint32_t flush_reserve(const RenderParams &p, int lane, uint32_t n, uint32_t rec_units, uint32_t head, bool &ok) {
+    const uint32_t units = 1u + rec_units * n;
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(p.pool_count, units);
     base = __shfl_sync(FULLMASK, base, 0);
-    if (base + units > p.pool_cap) return OVERFLOWED;
-    if (lane == 0) p.pool[base] = make_uint4(n, head, 0u, 0u);
+    ok = base + units <= p.pool_cap;
+    if (ok && lane == 0) p.pool[base] = make_uint4(n, head, 0u, 0u);
+    return base;
+}
+RT_DEV uint32_t flush_primary(const RenderParams &p, const CullShared &sm, int lane, uint32_t n, uint32_t head) {
+    if (n == 0 || head == OVERFLOWED) return head;
+    bool ok;
+    const uint32_t base = flush_reserve(p, lane, n, PU, head, ok);
+    if (!ok) return OVERFLOWED;
     for (uint32_t c = lane; c < n; c += 32) {
         const float4 a = sm.cand4[c];
+        const float2 e = sm.cand2[c];
         const uint32_t ax = __float_as_uint(a.x), ay = __float_as_uint(a.y), az = __float_as_uint(a.z);
-        uint4 *rec = p.pool + base + 1u + UNITS * c;
+        const uint32_t nvv = __float_as_uint(-a.w), rr = __float_as_uint(e.x);
+        const float4 box = screen_box(p, a, e.x);
+        uint4 *rec = p.pool + base + 1u + PU * c;
         rec[0] = make_uint4(ax, ax, ay, ay);
-        if (UNITS == 3) {
-            const float2 e = sm.cand2[c];
-            const uint32_t nvv = __float_as_uint(-a.w), rr = __float_as_uint(e.x);
-            rec[1] = make_uint4(az, az, nvv, nvv);
-            rec[2] = make_uint4(rr, rr, __float_as_uint(e.y), 0u);
-        } else {
-            const uint32_t rr = __float_as_uint(a.w);
-            rec[1] = make_uint4(az, az, rr, rr);
-        }
+        rec[1] = make_uint4(az, az, nvv, nvv);
+        rec[2] = make_uint4(rr, rr, __float_as_uint(e.y), 0u);
+        rec[3] = make_uint4(__float_as_uint(box.x), __float_as_uint(box.y), __float_as_uint(box.z), __float_as_uint(box.w));
+    }
+    return base;
+}
+RT_DEV uint32_t flush_shadow(const RenderParams &p, const CullShared &sm, const ShadowBeam &B, int lane, uint32_t n, uint32_t head) {
+    if (n == 0 || head == OVERFLOWED) return head;
+    bool ok;
+    const uint32_t base = flush_reserve(p, lane, n, SU, head, ok);
+    if (!ok) return OVERFLOWED;
+    for (uint32_t c = lane; c < n; c += 32) {
+        const float4 a = sm.cand4[c];  // {c, r*r}
+        const uint32_t ax = __float_as_uint(a.x), ay = __float_as_uint(a.y), az = __float_as_uint(a.z), rr = __float_as_uint(a.w);
+        // |c - origin| <= |c - P0| + len + rho for every shadow origin of the tile (beam_test(ShadowBeam))
+        const float qx = a.x - B.px, qy = a.y - B.py, qz = a.z - B.pz;
+        const float vmax = asqrt(fmaf(qx, qx, fmaf(qy, qy, qz * qz))) + B.len + B.rho;
+        // exact test passes => distance(c, shadow line) <= sqrt(rr + eps (vv + rr)); + 1e-5 for the f32
+        // projections onto (e1, e2) here and in K4 (|o|, |c| < 16: < 3e-6 each)
+        const float R = fmaf(asqrt(fmaf(EPS_DISC, fmaf(vmax, vmax, a.w), a.w)), 1.001f, 1e-5f);
+        const float cu = fmaf(a.x, p.lframe[0], fmaf(a.y, p.lframe[1], a.z * p.lframe[2]));
+        const float cv = fmaf(a.x, p.lframe[3], fmaf(a.y, p.lframe[4], a.z * p.lframe[5]));
+        uint4 *rec = p.pool + base + 1u + SU * c;
+        rec[0] = make_uint4(ax, ax, ay, ay);
+        rec[1] = make_uint4(az, az, rr, rr);
+        rec[2] = make_uint4(__float_as_uint(cu), __float_as_uint(cv), __float_as_uint(R * R), 0u);
     }
     return base;
 }
@@ -120,7 +190,7 @@ __global__ void __launch_bounds__(32 * P_WARPS) phase_cull_primary(const RenderP
     bool done;
     do {
         done = cull_run<true>(p, sm, pb, lane, cs);
-        head = flush_chunk<3>(p, sm, lane, cs.ncand, head);
+        head = flush_primary(p, sm, lane, cs.ncand, head);
         __syncwarp();
     } while (!done && head != OVERFLOWED);
     if (lane == 0) p.tile_hdr[ct] = make_uint4(head, NO_CHUNK, 0x7f800000u, 0u);
@@ -133,7 +203,7 @@ template <int SPP, int PXW, int PXH, int CW, int CH>
 __global__ void __launch_bounds__(32 * CW * CH, RT_PHASED_MINBLOCKS) phase_test_primary(const RenderParams p) {
     using G = Geo<SPP, PXW, PXH, CW, CH>;
     constexpr int S = G::S, NS = G::NS;
-    __shared__ uint4 stage[1 + 3 * T_CAND];  // the cull tile's first candidate chunk, shared by its pixel tiles
+    __shared__ uint4 stage[1 + PU * T_CAND];  // the cull tile's first candidate chunk, shared by its pixel tiles
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const G geo(p.width, p.row_count);
     // one block per cull tile, one warp per pixel tile of it
@@ -151,7 +221,7 @@ __global__ void __launch_bounds__(32 * CW * CH, RT_PHASED_MINBLOCKS) phase_test_
     const uint32_t head = p.tile_hdr[ct].x;
     if (head == NO_CHUNK) return;  // no candidate at all: K4 sees an empty hit range and never reads the winners
     if (head != OVERFLOWED) {      // stage the first chunk (almost always the only one) in shared memory
-        const uint32_t units = 1u + 3u * __ldg(&p.pool[head]).x;
+        const uint32_t units = 1u + PU * __ldg(&p.pool[head]).x;
         for (uint32_t u = threadIdx.x; u < units; u += blockDim.x) stage[u] = __ldg(&p.pool[head + u]);
     }
     __syncthreads();
@@ -174,38 +244,35 @@ __global__ void __launch_bounds__(32 * CW * CH, RT_PHASED_MINBLOCKS) phase_test_
             winner[s * 32 + lane] = bi;
         }
     } else {
-        // this lane's own block: a much narrower cone, used to pre-filter the tile's candidates
-        PrimaryBeam lb;
+        // Sample-coordinate rectangles of this lane's own block and of the warp's pixel tile: a
+        // candidate whose screen_box misses the rectangle cannot be hit by any of its rays.
+        constexpr float frac = G::FRAC;
+        float lx0, lx1, ly0, ly1, wx0, wx1, wy0, wy1;
         {
-            const float frac = (float)(SPP - 1) / (float)SPP;
             const uint32_t xh = min(bx + PXW, p.width) - 1u, jh = min(bj + PXH, p.row_count) - 1u;
             const float ya = (float)(image_row(p, bj)), yb = (float)(image_row(p, jh));
-            lb = make_primary_beam(p, (float)bx, (float)xh + frac, fminf(ya, yb), fmaxf(ya, yb) + frac);
+            lx0 = (float)bx, lx1 = (float)xh + frac, ly0 = fminf(ya, yb), ly1 = fmaxf(ya, yb) + frac;
         }
-        // the warp's pixel tile: between the cull tile's cone and the lane's
-        PrimaryBeam wb;
         {
-            const float frac = (float)(SPP - 1) / (float)SPP;
             const uint32_t xh = min(tile_x0 + G::TW, p.width) - 1u, jh = min(tile_j0 + G::TH, p.row_count) - 1u;
             const float ya = (float)(image_row(p, tile_j0)), yb = (float)(image_row(p, jh));
-            wb = make_primary_beam(p, (float)tile_x0, (float)xh + frac, fminf(ya, yb), fmaxf(ya, yb) + frac);
+            wx0 = (float)tile_x0, wx1 = (float)xh + frac, wy0 = fminf(ya, yb), wy1 = fmaxf(ya, yb) + frac;
         }
         // candidates c0..c1 (at most 32) of a chunk -> bit mask of those this LANE's block can see.
-        // First every lane tests ONE candidate against the warp tile's cone (ballot), then each lane
-        // tests the survivors against its own cone.
-        auto cand_test = [&](const PrimaryBeam &beam, uint32_t base, uint32_t c) {
-            const uint4 u0 = fetch(base, 1u + 3u * c), u1 = fetch(base, 2u + 3u * c), u2 = fetch(base, 3u + 3u * c);
-            const float4 af = make_float4(__uint_as_float(u0.x), __uint_as_float(u0.z), __uint_as_float(u1.x), -__uint_as_float(u1.z));
-            return lane_test(beam, af, __uint_as_float(u2.x));
+        // First every lane tests ONE candidate against the warp tile's rectangle (ballot), then each
+        // lane tests the survivors against its own.
+        auto cand_box = [&](uint32_t base, uint32_t c) {
+            const uint4 u = fetch(base, 4u + PU * c);
+            return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
         };
         auto chunk_mask = [&](uint32_t base, uint32_t c0, uint32_t c1) {
-            const bool w_ok = (c0 + lane < c1) && cand_test(wb, base, c0 + lane);
+            const bool w_ok = (c0 + lane < c1) && box_overlaps(cand_box(base, c0 + lane), wx0, wx1, wy0, wy1);
             uint32_t mask = 0;
             for (uint32_t wm = __ballot_sync(FULLMASK, w_ok); wm; wm &= wm - 1u) {
                 const uint32_t c = c0 + (uint32_t)__ffs((int)wm) - 1u;
-                if (lane_in && cand_test(lb, base, c)) mask |= 1u << (c - c0);
+                if (box_overlaps(cand_box(base, c), lx0, lx1, ly0, ly1)) mask |= 1u << (c - c0);
             }
-            return mask;
+            return lane_in ? mask : 0u;
         };
         // mask of the first 32 candidates of the first chunk: reused by every slot pair
         uint32_t mask0 = 0;
@@ -236,7 +303,7 @@ __global__ void __launch_bounds__(32 * CW * CH, RT_PHASED_MINBLOCKS) phase_test_
             // hot path: the first 32 candidates of the staged chunk, straight from shared memory
             for (uint32_t m = mask0; m; m &= m - 1u) {
                 const uint32_t c = (uint32_t)__ffs((int)m) - 1u;
-                test(stage[1u + 3u * c], stage[2u + 3u * c], stage[3u + 3u * c]);
+                test(stage[1u + PU * c], stage[2u + PU * c], stage[3u + PU * c]);
             }
             // cold path: the rest of the staged chunk and any further chunks of the chain
             for (uint32_t base = head; base != NO_CHUNK;) {
@@ -245,7 +312,7 @@ __global__ void __launch_bounds__(32 * CW * CH, RT_PHASED_MINBLOCKS) phase_test_
                 for (uint32_t c0 = (base == head) ? 32u : 0u; c0 < n; c0 += 32) {
                     for (uint32_t m = chunk_mask(base, c0, min(n, c0 + 32u)); m; m &= m - 1u) {
                         const uint32_t c = c0 + (uint32_t)__ffs((int)m) - 1u;
-                        test(fetch(base, 1u + 3u * c), fetch(base, 2u + 3u * c), fetch(base, 3u + 3u * c));
+                        test(fetch(base, 1u + PU * c), fetch(base, 2u + PU * c), fetch(base, 3u + PU * c));
                     }
                 }
                 base = hdr.y;
@@ -321,7 +388,7 @@ __global__ void __launch_bounds__(32 * P_WARPS) phase_cull_shadow(const RenderPa
     bool done;
     do {
         done = cull_run<false>(p, sm, sb, lane, cs);
-        head = flush_chunk<2>(p, sm, lane, cs.ncand, head);
+        head = flush_shadow(p, sm, sb, lane, cs.ncand, head);
         __syncwarp();
     } while (!done && head != OVERFLOWED);
     if (lane == 0) reinterpret_cast<uint32_t *>(&p.tile_hdr[ct])[1] = head;
@@ -334,7 +401,7 @@ template <int SPP, int PXW, int PXH, int CW, int CH, bool DIAG>
 __global__ void __launch_bounds__(32 * CW * CH, RT_PHASED_MINBLOCKS) phase_shade_store(const RenderParams p) {
     using G = Geo<SPP, PXW, PXH, CW, CH>;
     constexpr int S = G::S, NS = G::NS;
-    __shared__ uint4 stage[1 + 2 * T_CAND];  // the cull tile's first shadow-candidate chunk
+    __shared__ uint4 stage[1 + SU * T_CAND];  // the cull tile's first shadow-candidate chunk
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const G geo(p.width, p.row_count);
     // one block per cull tile, one warp per pixel tile of it
@@ -361,7 +428,7 @@ __global__ void __launch_bounds__(32 * CW * CH, RT_PHASED_MINBLOCKS) phase_shade
     const uint4 tile_hdr = p.tile_hdr[ct];
     const uint32_t head = tile_hdr.y;
     if (head < OVERFLOWED) {  // stage the first chunk (almost always the only one) in shared memory
-        const uint32_t units = 1u + 2u * __ldg(&p.pool[head]).x;
+        const uint32_t units = 1u + SU * __ldg(&p.pool[head]).x;
         for (uint32_t u = threadIdx.x; u < units; u += blockDim.x) stage[u] = __ldg(&p.pool[head + u]);
     }
     __syncthreads();
@@ -386,59 +453,77 @@ __global__ void __launch_bounds__(32 * CW * CH, RT_PHASED_MINBLOCKS) phase_shade
                 }
             }
         }
-    } else if (lane_in) {
+    } else {
+        // Every lane takes part (warp-wide ballots below); lanes outside the frame have no hits and store nothing.
         const V3x2 eye2 = v3x2s(eye), light2 = v3x2s(light), to_light2 = v3x2s(to_light);
-#ifndef RT_K4_UNROLL
-#define RT_K4_UNROLL 1
-#endif
-        constexpr int K4_UNROLL = RT_K4_UNROLL;
-#pragma unroll K4_UNROLL
-        for (int s0 = 0; s0 < S; s0 += 2) {  // two slots per pass: packed f32x2 arithmetic
-            const int s1 = (s0 + 1 < S) ? s0 + 1 : s0;
-            uint32_t x0, j0, x1, j1;
-            slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s0 / NS, x0, j0);
-            slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s1 / NS, x1, j1);
-            const V3x2 d = slot_dir2<SPP>(one, p, x0, image_row(p, j0), s0 % NS, x1,
-                                          image_row(p, j1), s1 % NS);
-            const uint32_t wi0 = winner[s0 * 32 + lane], wi1 = winner[s1 * 32 + lane];
-            const bool hit0 = wi0 != NO_HIT, hit1 = wi1 != NO_HIT;
-            const float4 w0 = __ldg(&p.sph[hit0 ? wi0 : 0u]), w1 = __ldg(&p.sph[hit1 ? wi1 : 0u]);
-            const V3x2 cen = V3x2{f2(w0.x, w1.x), f2(w0.y, w1.y), f2(w0.z, w1.z)};
-            const F2 rad = f2(w0.w, w1.w);
-            // the winner's distance again (primitive.rs:55-72), exactly as K2 computed it
-            const V3x2 v = vsub2(one, cen, eye2);
-            F2 dist = primary_distance2(one, v, f2neg(vdot2(one, v, v)), f2mul(rad, rad), d);
-            if (!hit0) dist.x = 1.0f;
-            if (!hit1) dist.y = 1.0f;
-            // primitive.rs:83 normal; render.rs:194 g; render.rs:199 shadow origin
-            const V3x2 nrm = vnormalized2(one, vadd2(one, eye2, vsub2(one, vmulf2(d, dist), cen)));
-            const F2 gg = vdot2(one, nrm, light2);
-            const V3x2 o = vadd2(one, vadd2(one, eye2, vmulf2(d, dist)), vmulf2(nrm, f2mul(dist, f2s(sqrt_eps))));
-            const V3x2 no = V3x2{f2neg(o.x), f2neg(o.y), f2neg(o.z)};
-            float g[2] = {hit0 ? gg.x : RT_INF, hit1 ? gg.y : RT_INF};
-            uint32_t pend = 0, occluded = 0;  // bit k: slot k still needs / has found an occluder
-            if (hit0 && !(gg.x >= 0.0f)) pend |= 1u;
-            if (hit1 && !(gg.y >= 0.0f) && s1 != s0) pend |= 2u;
-            if (head == OVERFLOWED) {  // per-lane walk, any-hit (render.rs:202-208)
+        const F2 e1a = f2(p.lframe[0], p.lframe[3]), e1b = f2(p.lframe[1], p.lframe[4]), e1c = f2(p.lframe[2], p.lframe[5]);
+        constexpr int GS = 4;  // slots per group: two packed pairs share one candidate pre-filter pass
+#pragma unroll 1
+        for (int g0 = 0; g0 < S; g0 += GS) {
+            // ---- A: hit point, normal, g and shadow origin of the group's slots (render.rs:188-199) ----
+            V3x2 no[2];           // minus the shadow origins, per pair
+            F2 nuv[2][2];         // minus their coordinates in the plane perpendicular to the light, per pair and slot
+            float g[GS];          // g = normal . light; +inf = no hit
+            uint32_t pend = 0, occluded = 0;  // bit 2k+i: slot i of pair k still needs / has found an occluder
+            uint32_t xs[GS], js[GS];
 #pragma unroll
-                for (int k = 0; k < 2; k++) {
-                    if ((pend >> k) & 1u) {
+            for (int k = 0; k < 2; k++) {
+                const int s0 = g0 + 2 * k, s1 = (s0 + 1 < S) ? s0 + 1 : s0;
+                if (s0 < S) {
+                    slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s0 / NS, xs[2 * k], js[2 * k]);
+                    slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s1 / NS, xs[2 * k + 1], js[2 * k + 1]);
+                    const V3x2 d = slot_dir2<SPP>(one, p, xs[2 * k], image_row(p, js[2 * k]), s0 % NS, xs[2 * k + 1],
+                                                  image_row(p, js[2 * k + 1]), s1 % NS);
+                    const uint32_t wi0 = winner[s0 * 32 + lane], wi1 = winner[s1 * 32 + lane];
+                    const bool hit0 = wi0 != NO_HIT, hit1 = wi1 != NO_HIT;
+                    const float4 w0 = __ldg(&p.sph[hit0 ? wi0 : 0u]), w1 = __ldg(&p.sph[hit1 ? wi1 : 0u]);
+                    const V3x2 cen = V3x2{f2(w0.x, w1.x), f2(w0.y, w1.y), f2(w0.z, w1.z)};
+                    const F2 rad = f2(w0.w, w1.w);
+                    // the winner's distance again (primitive.rs:55-72), exactly as K2 computed it
+                    const V3x2 v = vsub2(one, cen, eye2);
+                    F2 dist = primary_distance2(one, v, f2neg(vdot2(one, v, v)), f2mul(rad, rad), d);
+                    if (!hit0) dist.x = 1.0f;
+                    if (!hit1) dist.y = 1.0f;
+                    // primitive.rs:83 normal; render.rs:194 g; render.rs:199 shadow origin
+                    const V3x2 nrm = vnormalized2(one, vadd2(one, eye2, vsub2(one, vmulf2(d, dist), cen)));
+                    const F2 gg = vdot2(one, nrm, light2);
+                    const V3x2 o = vadd2(one, vadd2(one, eye2, vmulf2(d, dist)), vmulf2(nrm, f2mul(dist, f2s(sqrt_eps))));
+                    no[k] = V3x2{f2neg(o.x), f2neg(o.y), f2neg(o.z)};
+                    nuv[k][0] = f2fma(f2s(no[k].x.x), e1a, f2fma(f2s(no[k].y.x), e1b, f2mul(f2s(no[k].z.x), e1c)));
+                    nuv[k][1] = f2fma(f2s(no[k].x.y), e1a, f2fma(f2s(no[k].y.y), e1b, f2mul(f2s(no[k].z.y), e1c)));
+                    g[2 * k] = hit0 ? gg.x : RT_INF;
+                    g[2 * k + 1] = hit1 ? gg.y : RT_INF;
+                    if (hit0 && !(gg.x >= 0.0f)) pend |= 1u << (2 * k);
+                    if (hit1 && !(gg.y >= 0.0f) && s1 != s0) pend |= 2u << (2 * k);
+                } else {
+                    no[k] = V3x2{f2s(0.0f), f2s(0.0f), f2s(0.0f)};
+                    nuv[k][0] = nuv[k][1] = f2s(0.0f);
+                    g[2 * k] = g[2 * k + 1] = RT_INF;
+                    xs[2 * k] = xs[2 * k + 1] = js[2 * k] = js[2 * k + 1] = 0xffffffffu;
+                }
+            }
+            // ---- B: shadow rays {pos: o, dir: -light} against the tile's candidates (render.rs:202-208) ----
+            if (head == OVERFLOWED) {  // per-lane walk, any-hit
+#pragma unroll
+                for (int i = 0; i < GS; i++) {
+                    if ((pend >> i) & 1u) {
                         float sh = RT_INF;
                         uint32_t dummy = 0;
-                        lane_traverse<true>(p.sph, p.skip, p.n_nodes, k ? hi(o) : lo(o), to_light, sh, dummy);
-                        if (sh != RT_INF) occluded |= 1u << k;
+                        const V3x2 o = V3x2{f2neg(no[i >> 1].x), f2neg(no[i >> 1].y), f2neg(no[i >> 1].z)};
+                        lane_traverse<true>(p.sph, p.skip, p.n_nodes, (i & 1) ? hi(o) : lo(o), to_light, sh, dummy);
+                        if (sh != RT_INF) occluded |= 1u << i;
                     }
                 }
                 pend = 0;
             }
-            auto shadow_test = [&](const uint4 u0, const uint4 u1) {
+            // exact any-hit test of pair k against one candidate (primitive.rs:56-68)
+            auto shadow_test = [&](const int k, const uint4 u0, const uint4 u1) {
                 V3x2 cc;
                 cc.x = f2(__uint_as_float(u0.x), __uint_as_float(u0.y));
                 cc.y = f2(__uint_as_float(u0.z), __uint_as_float(u0.w));
                 cc.z = f2(__uint_as_float(u1.x), __uint_as_float(u1.y));
                 const F2 rr = f2(__uint_as_float(u1.z), __uint_as_float(u1.w));
-                // primitive.rs:56-58 for the shadow rays {pos: o, dir: -light}
-                const V3x2 sv = vadd2(one, cc, no);  // center - ray.pos
+                const V3x2 sv = vadd2(one, cc, no[k]);  // center - ray.pos
                 const F2 b = vdot2(one, sv, to_light2);
                 const F2 disc = f2add(one, f2sub(one, f2mul(b, b), vdot2(one, sv, sv)), rr);
                 // finite iff disc >= 0 and !(b + sqrt(disc) < 0) (primitive.rs:60-68); b >= 0 settles the latter
@@ -448,46 +533,88 @@ __global__ void __launch_bounds__(32 * CW * CH, RT_PHASED_MINBLOCKS) phase_shade
                     f0 = f0 && !(t2.x < 0.0f);
                     f1 = f1 && !(t2.y < 0.0f);
                 }
-                const uint32_t f = ((f0 ? 1u : 0u) | (f1 ? 2u : 0u)) & pend;
+                const uint32_t f = (((f0 ? 1u : 0u) | (f1 ? 2u : 0u)) << (2 * k)) & pend;
                 pend &= ~f;
                 occluded |= f;
             };
-            if (head < OVERFLOWED) {
-                // hot path: the staged chunk, straight from shared memory
-                const uint32_t n0 = stage[0].x;
-                for (uint32_t ci = 0; ci < n0 && pend; ci++) shadow_test(stage[1u + 2u * ci], stage[2u + 2u * ci]);
-                // cold path: further chunks of the chain
-                for (uint32_t base = stage[0].y; base != NO_CHUNK && pend;) {
-                    const uint4 hdr = __ldg(&p.pool[base]);
-                    for (uint32_t ci = 0; ci < hdr.x && pend; ci++)
-                        shadow_test(__ldg(&p.pool[base + 1u + 2u * ci]), __ldg(&p.pool[base + 2u + 2u * ci]));
+            if (__ballot_sync(FULLMASK, pend != 0u) != 0u && head < OVERFLOWED) {
+                // Rectangle of the warp's pending shadow origins in the plane perpendicular to the light.
+                float ulo = RT_INF, uhi = -RT_INF, vlo = RT_INF, vhi = -RT_INF;
+#pragma unroll
+                for (int i = 0; i < GS; i++) {
+                    if ((pend >> i) & 1u) {
+                        const F2 q = nuv[i >> 1][i & 1];
+                        ulo = fminf(ulo, -q.x), uhi = fmaxf(uhi, -q.x), vlo = fminf(vlo, -q.y), vhi = fmaxf(vhi, -q.y);
+                    }
+                }
+                ulo = warp_min_f(ulo), uhi = warp_max_f(uhi), vlo = warp_min_f(vlo), vhi = warp_max_f(vhi);
+                const uint32_t first = head;
+                for (uint32_t base = first; base != NO_CHUNK;) {
+                    const bool staged = base == first;
+                    const uint4 hdr = staged ? stage[0] : __ldg(&p.pool[base]);
+                    auto unit = [&](uint32_t off) { return staged ? stage[off] : __ldg(&p.pool[base + off]); };
+                    for (uint32_t c0 = 0; c0 < hdr.x; c0 += 32) {
+                        // warp level: lane tests candidate c0 + lane (disc vs rectangle)
+                        bool w_ok = false;
+                        if (c0 + lane < hdr.x) {
+                            const uint4 u = unit(3u + SU * (c0 + lane));
+                            const float cu = __uint_as_float(u.x), cv = __uint_as_float(u.y);
+                            const float du = fmaxf(fmaxf(ulo - cu, cu - uhi), 0.0f), dv = fmaxf(fmaxf(vlo - cv, cv - vhi), 0.0f);
+                            w_ok = du * du + dv * dv <= __uint_as_float(u.z);
+                        }
+                        // lane level: the survivors against each pending slot (packed over the two plane coordinates)
+                        uint32_t m0 = 0, m1 = 0;
+                        for (uint32_t wm = __ballot_sync(FULLMASK, w_ok); wm; wm &= wm - 1u) {
+                            const uint32_t b = (uint32_t)__ffs((int)wm) - 1u;
+                            const uint4 u = unit(3u + SU * (c0 + b));
+                            const F2 cuv = f2(__uint_as_float(u.x), __uint_as_float(u.y));
+                            const float r2 = __uint_as_float(u.z);
+                            const F2 d00 = __fadd2_rn(cuv, nuv[0][0]), d01 = __fadd2_rn(cuv, nuv[0][1]);
+                            const F2 d10 = __fadd2_rn(cuv, nuv[1][0]), d11 = __fadd2_rn(cuv, nuv[1][1]);
+                            const F2 q00 = f2mul(d00, d00), q01 = f2mul(d01, d01), q10 = f2mul(d10, d10), q11 = f2mul(d11, d11);
+                            const bool h0 = ((pend & 1u) && q00.x + q00.y <= r2) || ((pend & 2u) && q01.x + q01.y <= r2);
+                            const bool h1 = ((pend & 4u) && q10.x + q10.y <= r2) || ((pend & 8u) && q11.x + q11.y <= r2);
+                            if (h0) m0 |= 1u << b;
+                            if (h1) m1 |= 1u << b;
+                        }
+                        // exact tests of each pair's survivors
+                        for (; m0 && (pend & 3u); m0 &= m0 - 1u) {
+                            const uint32_t c = c0 + (uint32_t)__ffs((int)m0) - 1u;
+                            shadow_test(0, unit(1u + SU * c), unit(2u + SU * c));
+                        }
+                        for (; m1 && (pend & 12u); m1 &= m1 - 1u) {
+                            const uint32_t c = c0 + (uint32_t)__ffs((int)m1) - 1u;
+                            shadow_test(1, unit(1u + SU * c), unit(2u + SU * c));
+                        }
+                    }
                     base = hdr.y;
+                    if (__ballot_sync(FULLMASK, pend != 0u) == 0u) break;
                 }
             }
-            // accumulate in reference sample order (render.rs:236-250), quantise, store (render.rs:92-109)
+            // ---- C: accumulate in reference sample order (render.rs:236-250), quantise, store (render.rs:92-109) ----
 #pragma unroll
-            for (int k = 0; k < 2; k++) {
-                const int s = s0 + k;
+            for (int i = 0; i < GS; i++) {
+                const int s = g0 + i;
                 if (s < S) {
-                    const int pi = s / NS, smp = s % NS;
-                    const uint32_t x = k ? x1 : x0, j = k ? j1 : j0;
+                    const int smp = s % NS;
+                    const uint32_t x = xs[i], j = js[i];
                     const bool inside = x < p.width && j < p.row_count;
                     if (smp == 0) {
                         c = v3(0.0f, 0.0f, 0.0f);
                         alpha = 0.0f;
                     }
                     uint8_t kind;
-                    if (g[k] == RT_INF) {  // render.rs:190-193
+                    if (g[i] == RT_INF) {  // render.rs:190-193
                         c = vadd(c, K_background);
                         kind = K_BACKGROUND;
-                    } else if (g[k] >= 0.0f) {  // render.rs:195-198
+                    } else if (g[i] >= 0.0f) {  // render.rs:195-198
                         c = vadd(c, K_ambient);
                         kind = K_AWAY;
                         if (DIAG && inside) n_hits++;
                     } else {
                         if (DIAG && inside) n_hits++, n_shadow++;
-                        const float ng = -g[k];
-                        if (!((occluded >> k) & 1u)) {  // render.rs:208-210
+                        const float ng = -g[i];
+                        if (!((occluded >> i) & 1u)) {  // render.rs:208-210
                             c = vadd(vadd(c, vmulf(K_object, ng)), K_ambient);
                             alpha = fadd(alpha, 1.0f);
                             kind = K_LIT;
@@ -496,7 +623,6 @@ __global__ void __launch_bounds__(32 * CW * CH, RT_PHASED_MINBLOCKS) phase_shade
                             kind = K_SHADOWED;
                         }
                     }
-                    (void)pi;
                     if (DIAG && p.kinds && inside) p.kinds[((size_t)j * p.width + x) * NS + smp] = kind;
                     if (smp == NS - 1 && inside) {
                         const V3 q = vmulf(c, recip);

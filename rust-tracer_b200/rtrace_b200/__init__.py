@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "rt_scene_counts", "rt_scene_export_nodes", "rt_flatten_pyramid_host", "rt_scene_light", "rt_scene_eye",
     "rt_scene_device", "rt_render_region", "rt_render_rows", "rt_render_row_blocks", "rt_render_frame", "rt_render_sweep", "rt_render_sweep_rgb",
     "rt_render_frame_multi",
-    "rt_count_rays", "rt_trace_rays", "rt_measure_fp32_peak", "rt_microbench_fp32", "rt_selftest_math", "rt_host_alloc", "rt_host_free", "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_memcpy",
+    "rt_count_rays", "rt_trace_rays", "rt_measure_fp32_peak", "rt_microbench_fp32", "rt_selftest_math", "rt_debug_phased_tiles", "rt_host_alloc", "rt_host_free", "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_memcpy",
 ]
 
 
@@ -360,6 +360,17 @@ def selftest_math(n=1 << 24, seed=1):
     m = (C.c_uint64 * 6)()
     _check(lib().rt_selftest_math(n, seed, m))
     return tuple(int(v) for v in m)
+
+
+def debug_phased_tiles(scene):
+    """(n_tiles, 2) uint32 array: primary / shadow candidates per cull tile of the last PHASED frame."""
+    n = C.c_uint32()
+    L = lib()
+    L.rt_debug_phased_tiles.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p]
+    _check(L.rt_debug_phased_tiles(scene.handle, 0, C.byref(n), None))
+    out = np.zeros((n.value, 2), dtype=np.uint32)
+    _check(L.rt_debug_phased_tiles(scene.handle, n.value, C.byref(n), out.ctypes.data))
+    return out
 
 
 def device_alloc(nbytes):
