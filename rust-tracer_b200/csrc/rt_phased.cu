@@ -31,9 +31,14 @@ namespace rt {
 static constexpr uint32_t NO_CHUNK = 0xffffffffu;
 static constexpr uint32_t OVERFLOWED = 0xfffffffeu;
 static constexpr int P_WARPS = 4;  // warps per block in every phase (independent warps)
-#ifndef RT_PHASED_MINBLOCKS
-#define RT_PHASED_MINBLOCKS 1
+// K2 / K4 are latency-bound below ~32 resident warps per SM (ncu: 4 blocks of 100 registers -> 49 %
+// issue-active on C3; capped at 64 registers -> 8 blocks of 4 warps, a few bytes of spill, 1.2x faster).
+#ifndef RT_PHASED_WARPS_PER_SM
+#define RT_PHASED_WARPS_PER_SM 32
 #endif
+constexpr int phased_min_blocks(int warps_per_block) {
+    return RT_PHASED_WARPS_PER_SM / warps_per_block > 0 ? RT_PHASED_WARPS_PER_SM / warps_per_block : 1;
+}
 
 struct CullShared {
     float4 cand4[T_CAND];
@@ -200,7 +205,7 @@ __global__ void __launch_bounds__(32 * P_WARPS) phase_cull_primary(const RenderP
 // K2: exact closest-hit tests, one warp per pixel tile
 // ---------------------------------------------------------------------------
 template <int SPP, int PXW, int PXH, int CW, int CH>
-__global__ void __launch_bounds__(32 * CW * CH, RT_PHASED_MINBLOCKS) phase_test_primary(const RenderParams p) {
+__global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phase_test_primary(const RenderParams p) {
     using G = Geo<SPP, PXW, PXH, CW, CH>;
     constexpr int S = G::S, NS = G::NS;
     __shared__ uint4 stage[1 + PU * T_CAND];  // the cull tile's first candidate chunk, shared by its pixel tiles
@@ -398,7 +403,7 @@ __global__ void __launch_bounds__(32 * P_WARPS) phase_cull_shadow(const RenderPa
 // K4: shading, shadow tests, accumulation, store; one warp per pixel tile
 // ---------------------------------------------------------------------------
 template <int SPP, int PXW, int PXH, int CW, int CH, bool DIAG>
-__global__ void __launch_bounds__(32 * CW * CH, RT_PHASED_MINBLOCKS) phase_shade_store(const RenderParams p) {
+__global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phase_shade_store(const RenderParams p) {
     using G = Geo<SPP, PXW, PXH, CW, CH>;
     constexpr int S = G::S, NS = G::NS;
     __shared__ uint4 stage[1 + SU * T_CAND];  // the cull tile's first shadow-candidate chunk

@@ -9,7 +9,7 @@ for shape in ${SHAPES:-0 1}; do
   RTRACE_TILE_SHAPE=$shape timeout 300 python tools/gpu_matrix.py ${VARIANTS:-4} ${CASES:-c1,c2,c2_l9,c3_l9,c4_l9,c3_l10} >> gpurun_out/matrix.jsonl 2>&1
 done
 cat gpurun_out/matrix.jsonl
-timeout 300 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches_iter.csv python tools/gpu_matrix.py 4 c2 > /dev/null 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches_iter.csv python tools/gpu_matrix.py 4 ${NCU_CASE:-c2} > /dev/null 2>&1
 python - <<'PY'
 import csv
 rows=[r for r in csv.reader(open('gpurun_out/launches_iter.csv')) if len(r)>5]
