@@ -282,16 +282,24 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
         // mask of the first 32 candidates of the first chunk: reused by every slot pair
         uint32_t mask0 = 0;
         if (head != NO_CHUNK) mask0 = chunk_mask(head, 0u, min(stage[0].x, 32u));
+        // GP packed pairs (two slots each) per pass: every candidate record is loaded once for all of them and
+        // the pairs' dependency chains interleave.
+        constexpr int GP = (S >= 4) ? 2 : 1;
 #pragma unroll 1
-        for (int s0 = 0; s0 < S; s0 += 2) {  // two slots per pass: packed f32x2 arithmetic
-            const int s1 = (s0 + 1 < S) ? s0 + 1 : s0;
-            uint32_t x0, j0, x1, j1;
-            slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s0 / NS, x0, j0);
-            slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s1 / NS, x1, j1);
-            const V3x2 d = slot_dir2<SPP>(one, p, x0, image_row(p, j0), s0 % NS, x1,
-                                          image_row(p, j1), s1 % NS);
-            F2 bd = f2s(RT_INF);
-            uint32_t bi0 = NO_HIT, bi1 = NO_HIT;
+        for (int g0 = 0; g0 < S; g0 += 2 * GP) {
+            V3x2 d[GP];
+            F2 bd[GP];
+            uint32_t bi[GP][2];
+#pragma unroll
+            for (int k = 0; k < GP; k++) {
+                const int s0 = min(g0 + 2 * k, S - 1), s1 = min(s0 + 1, S - 1);  // a pair past the end repeats the last slot
+                uint32_t x0, j0, x1, j1;
+                slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s0 / NS, x0, j0);
+                slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s1 / NS, x1, j1);
+                d[k] = slot_dir2<SPP>(one, p, x0, image_row(p, j0), s0 % NS, x1, image_row(p, j1), s1 % NS);
+                bd[k] = f2s(RT_INF);
+                bi[k][0] = bi[k][1] = NO_HIT;
+            }
             auto test = [&](const uint4 u0, const uint4 u1, const uint4 u2) {
                 V3x2 v;
                 v.x = f2(__uint_as_float(u0.x), __uint_as_float(u0.y));
@@ -300,10 +308,13 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
                 const F2 nvv = f2(__uint_as_float(u1.z), __uint_as_float(u1.w));
                 const F2 rr = f2(__uint_as_float(u2.x), __uint_as_float(u2.y));
                 const uint32_t idx = u2.z;
-                const F2 dist = primary_distance2(one, v, nvv, rr, d);
-                // primitive.rs:79 + pre-order visiting: strictly closer wins, ties -> lowest index
-                if (dist.x < bd.x || (dist.x == bd.x && idx < bi0 && bi0 != NO_HIT)) bd.x = dist.x, bi0 = idx;
-                if (dist.y < bd.y || (dist.y == bd.y && idx < bi1 && bi1 != NO_HIT)) bd.y = dist.y, bi1 = idx;
+#pragma unroll
+                for (int k = 0; k < GP; k++) {
+                    const F2 dist = primary_distance2(one, v, nvv, rr, d[k]);
+                    // primitive.rs:79 + pre-order visiting: strictly closer wins, ties -> lowest index
+                    if (dist.x < bd[k].x || (dist.x == bd[k].x && idx < bi[k][0] && bi[k][0] != NO_HIT)) bd[k].x = dist.x, bi[k][0] = idx;
+                    if (dist.y < bd[k].y || (dist.y == bd[k].y && idx < bi[k][1] && bi[k][1] != NO_HIT)) bd[k].y = dist.y, bi[k][1] = idx;
+                }
             };
             // hot path: the first 32 candidates of the staged chunk, straight from shared memory
             for (uint32_t m = mask0; m; m &= m - 1u) {
@@ -322,11 +333,17 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
                 }
                 base = hdr.y;
             }
-            winner[s0 * 32 + lane] = bi0;
-            if (bi0 != NO_HIT) tmin = fminf(tmin, fabsf(bd.x)), tmax = fmaxf(tmax, fabsf(bd.x));
-            if (s1 != s0) {
-                winner[s1 * 32 + lane] = bi1;
-                if (bi1 != NO_HIT) tmin = fminf(tmin, fabsf(bd.y)), tmax = fmaxf(tmax, fabsf(bd.y));
+#pragma unroll
+            for (int k = 0; k < GP; k++) {
+                const int s0 = g0 + 2 * k, s1 = s0 + 1;
+                if (s0 < S) {
+                    winner[s0 * 32 + lane] = bi[k][0];
+                    if (bi[k][0] != NO_HIT) tmin = fminf(tmin, fabsf(bd[k].x)), tmax = fmaxf(tmax, fabsf(bd[k].x));
+                }
+                if (s1 < S) {
+                    winner[s1 * 32 + lane] = bi[k][1];
+                    if (bi[k][1] != NO_HIT) tmin = fminf(tmin, fabsf(bd[k].y)), tmax = fmaxf(tmax, fabsf(bd[k].y));
+                }
             }
         }
     }
@@ -582,14 +599,15 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
                             if (h0) m0 |= 1u << b;
                             if (h1) m1 |= 1u << b;
                         }
-                        // exact tests of each pair's survivors
-                        for (; m0 && (pend & 3u); m0 &= m0 - 1u) {
-                            const uint32_t c = c0 + (uint32_t)__ffs((int)m0) - 1u;
-                            shadow_test(0, unit(1u + SU * c), unit(2u + SU * c));
-                        }
-                        for (; m1 && (pend & 12u); m1 &= m1 - 1u) {
-                            const uint32_t c = c0 + (uint32_t)__ffs((int)m1) - 1u;
-                            shadow_test(1, unit(1u + SU * c), unit(2u + SU * c));
+                        // exact tests of the survivors (both pairs per candidate: one record load, two
+                        // independent dependency chains)
+                        if (!(pend & 3u)) m0 = 0;
+                        if (!(pend & 12u)) m1 = 0;
+                        for (uint32_t m = m0 | m1; m && pend; m &= m - 1u) {
+                            const uint32_t c = c0 + (uint32_t)__ffs((int)m) - 1u;
+                            const uint4 u0 = unit(1u + SU * c), u1 = unit(2u + SU * c);
+                            shadow_test(0, u0, u1);
+                            shadow_test(1, u0, u1);
                         }
                     }
                     base = hdr.y;
@@ -686,7 +704,7 @@ void rt_phased_scratch(uint32_t width, uint32_t rows, uint32_t spp, int shape, s
     }
     switch (spp) {
         case 1:
-            if (shape == 1) RT_GEO(1, 2, 2, 4, 4) else if (shape == 2) RT_GEO(1, 4, 2, 1, 2) else if (shape == 3) RT_GEO(1, 2, 1, 2, 4) else if (shape == 4) RT_GEO(1, 2, 1, 1, 2) else RT_GEO(1, 2, 2, 2, 2)
+            if (shape == 1) RT_GEO(1, 2, 2, 4, 4) else if (shape == 5) RT_GEO(1, 2, 2, 4, 2) else if (shape == 6) RT_GEO(1, 2, 2, 2, 4) else if (shape == 2) RT_GEO(1, 4, 2, 1, 2) else if (shape == 3) RT_GEO(1, 2, 1, 2, 4) else if (shape == 4) RT_GEO(1, 2, 1, 1, 2) else RT_GEO(1, 2, 2, 2, 2)
             break;
         case 2:
             if (shape == 1) RT_GEO(2, 1, 1, 4, 4) else RT_GEO(2, 1, 1, 2, 2)
@@ -711,6 +729,8 @@ cudaError_t rt_launch_render_phased(bool diag, const RenderParams &p, cudaStream
     // shape 0: cull tile = 2x2 pixel tiles; shape 1: 4x4 pixel tiles
     switch (p.spp) {
         case 1:
+            if (shape == 5) return launch_phased<1, 2, 2, 4, 2>(diag, p, stream);  // 64x16 cull tile
+            if (shape == 6) return launch_phased<1, 2, 2, 2, 4>(diag, p, stream);  // 32x32 cull tile
             if (shape == 2) return launch_phased<1, 4, 2, 1, 2>(diag, p, stream);  // 8 pixels per lane
             if (shape == 3) return launch_phased<1, 2, 1, 2, 4>(diag, p, stream);  // 2 pixels per lane, 32x16 cull tile
             if (shape == 4) return launch_phased<1, 2, 1, 1, 2>(diag, p, stream);  // 2 pixels per lane, 16x8 cull tile
