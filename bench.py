@@ -360,9 +360,12 @@ def main():
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         fb_bytes = my_rows * width * 4
-        traffic = None
+        traffic, ncu_facts = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "latest_summary.json"))).get(args.workload, {}).get("dram_bytes_per_launch")
+            summ = json.load(open(os.path.join(ROOT, "profiles", "latest_summary.json"))).get(args.workload, {})
+            traffic = summ.get("dram_bytes_per_launch")
+            ncu_facts = {k: summ[k] for k in ("dominant_kernel", "fma_pipe_cycles_active_pct", "issue_active_pct",
+                                              "warp_instructions_per_frame", "source") if k in summ} or None
         except Exception:
             pass
         out = {
@@ -383,6 +386,7 @@ def main():
             "roofline": {
                 "bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf, "traffic": traffic,
+                "ncu": ncu_facts,   # what the hardware actually did (committed ncu capture), next to the reference-work figure
                 "note": "path is FP32-issue bound, not HBM/tensor (SURVEY 8d): achieved = rays/launch x %.1f "
                         "algorithmic flop/ray of REFERENCE work (%s) / event time; peak = %s" % (fpr, fpr_src, peak_src),
                 "hbm": {"achieved": fb_bytes / (ms_per_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",

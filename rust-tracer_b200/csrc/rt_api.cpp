@@ -248,17 +248,18 @@ int kernel_variant(const rt::RenderParams &p) {
     }
     if (!tile_ok) return RT_KERNEL_LANE;
     // AUTO (measured on B200, profiles/r01_variant_matrix.json):
-    //  * when the smallest leaves project to less than ~2.5 sample spacings the exact test is
+    //  * when the smallest leaves project to less than ~1.5 sample spacings the exact test is
     //    rounding noise, the cull must inflate them several-fold and the per-lane
-    //    walk, which needs no inflation, wins;
-    //  * frames with few pixel tiles cannot fill the GPU four times over: the fused kernel wins;
-    //  * otherwise the four homogeneous launches win.
+    //    walk, which needs no inflation, wins (640x480 level 8: 0.14 vs 0.30 ms);
+    //  * frames with few pixel tiles cannot fill the GPU four times over: the fused kernel wins
+    //    (1280x720: 0.137 vs 0.147 ms);
+    //  * otherwise the four homogeneous launches win (1080p and up, every level <= 10).
     const float dx = p.eye[0] - p.scene_center[0], dy = p.eye[1] - p.scene_center[1], dz = p.eye[2] - p.scene_center[2];
     const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
     const float leaf_px = p.leaf_rmin * (float)p.width / fmaxf(dist, 1e-6f) * (float)p.spp;
-    if (leaf_px < 2.5f) return RT_KERNEL_LANE;
+    if (leaf_px < 1.5f) return RT_KERNEL_LANE;
     const uint64_t pixel_tiles = (uint64_t)p.width * p.row_count / (p.spp == 1 ? 128u : 32u);  // one warp each
-    return pixel_tiles < 40000 ? RT_KERNEL_TILE : RT_KERNEL_PHASED;
+    return pixel_tiles < 8000 ? RT_KERNEL_TILE : RT_KERNEL_PHASED;
 }
 
 int tile_shape() {
