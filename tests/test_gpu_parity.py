@@ -319,3 +319,29 @@ def test_blocked_rows_and_absolute_addressing(rt, oracle_scene8, gpu_scene8):
     assert np.array_equal(band.cpu().numpy(), ref[partition.block_band_rows(h, 1, 3, 16)])
     with pytest.raises(rt.RtError):
         rt.Renderer.render_row_blocks(o, gpu_scene8, 0, 48, 12, 10, band.data_ptr())   # block not a power of two
+
+
+@pytest.mark.parametrize("kw,frames", [
+    (dict(), (7, 41, 88)),                               # Scene::default from three orbit positions
+    (dict(light=(-4.0, -0.2, 0.1)), (0, 23)),            # light nearly sideways
+    (dict(light=(0.3, 2.0, 0.5)), (0, 100)),             # light from below
+    (dict(light=(0.0, 0.0, -1.0)), (0, 60)),             # light along / against the view axis
+])
+def test_phased_prefilters_hold_for_cameras_and_lights(rt, oracle, kw, frames):
+    """PHASED regime (tiles small against the spheres): the image-space boxes of the primary candidates
+    are computed in camera coordinates and the shadow discs in the plane perpendicular to the light, so
+    rotated cameras and other lights must give the oracle's bytes too."""
+    w, h, level = 1280, 720, 8
+    gs, os_ = rt.Scene(level=level, **kw), oracle.Scene(level=level, **kw)
+    rt.set_variant(rt.VARIANT_PHASED)
+    try:
+        for i, f in enumerate(frames):
+            spp = 1 + (i % 2)
+            gc, oc = rt.orbit_camera(f, 120), oracle.Camera()
+            for k in ("eye", "right", "up", "forward"):
+                getattr(oc, k)[:] = getattr(gc, k)[:]
+            ref, _ = os_.render(w, h, spp, camera=oc)
+            img = rt.Renderer.render(rt.RenderOptions(w, h, spp), gs, camera=gc)
+            assert_same(img, ref, "%s orbit frame %d spp %d" % (kw, f, spp))
+    finally:
+        rt.set_variant(rt.VARIANT_AUTO)
