@@ -51,6 +51,7 @@ const char *USAGE =
     "        --level <L>                        Depth of the sphere pyramid [default: 8]\n"
     "        --gpus <N>                         GPUs to render on; rows are interleaved [default: 1 or RTRACE_GPUS]\n"
     "        --frames <K>                       Render a K-frame orbit of the camera [default: 1]\n"
+    "        --format <ppm|tga>                 File contents: the reference's binary PPM, or a real TGA [default: ppm]\n"
     "        --stats                            Print a timing summary to stderr\n"
     "\n"
     "ARGS:\n"
@@ -88,7 +89,7 @@ unsigned long long parse_or_panic(const std::string &s, unsigned long long max, 
 }
 
 struct Args {
-    std::string width, height, ssp, numcores, output, level, gpus, frames;
+    std::string width, height, ssp, numcores, output, level, gpus, frames, format;
     bool has_output = false, stats = false;
 };
 
@@ -100,7 +101,7 @@ Args parse_args(int argc, char **argv) {
     };
     const Opt opts[] = {{"--width", &Args::width},   {"--height", &Args::height}, {"--samples-per-pixel", &Args::ssp},
                         {"--num-cores", &Args::numcores}, {"--level", &Args::level},   {"--gpus", &Args::gpus},
-                        {"--frames", &Args::frames}};
+                        {"--frames", &Args::frames}, {"--format", &Args::format}};
     bool only_positional = false;
     for (int i = 1; i < argc; i++) {
         std::string arg = argv[i];
@@ -226,6 +227,9 @@ int main(int argc, char **argv) {
     unsigned frames = (unsigned)parse_or_panic(args.frames.empty() ? "1" : args.frames, 100000, "frames");
     if (gpus < 1) gpus = 1;
     if (frames < 1) frames = 1;
+    if (!args.format.empty() && args.format != "ppm" && args.format != "tga")
+        usage_error("'" + args.format + "' isn't a valid value for '--format <ppm|tga>'");
+    const bool real_tga = args.format == "tga";
     if (options.width == 0 || options.height == 0) {
         fprintf(stderr, "thread 'main' panicked at 'width and height must be at least 1'\n");
         return 101;
@@ -258,9 +262,13 @@ int main(int argc, char **argv) {
             // frames arrive as RGB8: exactly the body PPMStdoutRGBABufferWriter would write (render.rs:377-397)
             Renderer::render_sweep(options, scene, cams, [&](uint32_t f, const uint8_t *rgb, size_t len) {
                 output = open_output(f);
-                fprintf(output.f, "P6\n%u %u\n255\n", (unsigned)options.width, (unsigned)options.height);
-                if (fwrite(rgb, 1, len, output.f) != len) throw Panic("write_all failed");
-                fflush(output.f);
+                if (real_tga) {
+                    write_tga(output.f, options.width, options.height, rgb, (size_t)options.width * 3, 3);
+                } else {
+                    fprintf(output.f, "P6\n%u %u\n255\n", (unsigned)options.width, (unsigned)options.height);
+                    if (fwrite(rgb, 1, len, output.f) != len) throw Panic("write_all failed");
+                    fflush(output.f);
+                }
                 if (fp) fclose(fp), fp = nullptr;
             }, &st, true);
             render_ms += std::chrono::duration<double, std::milli>(clk::now() - r0).count();
@@ -271,7 +279,10 @@ int main(int argc, char **argv) {
                 rt_camera cam = orbit_camera(f, frames);
                 rt_stats st;
                 {
-                    PPMStdoutRGBABufferWriter writer(true, &output);
+                    std::unique_ptr<RGBABufferWriter> sink;
+                    if (real_tga) sink.reset(new TGARGBABufferWriter(&output));
+                    else sink.reset(new PPMStdoutRGBABufferWriter(true, &output));
+                    RGBABufferWriter &writer = *sink;
                     auto r0 = clk::now();
                     Renderer::render(options, scene, writer, frames > 1 ? &cam : nullptr, &st);
                     render_ms += std::chrono::duration<double, std::milli>(clk::now() - r0).count();

@@ -8,6 +8,7 @@
 // GPU and a strided gather of row bands.  The writer trait is kept as the seam
 // for output sinks (render.rs:20-30).
 #pragma once
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -107,8 +108,10 @@ struct FileOrAnyWriter {
 
 // render.rs:319-434: P6 (rgb) or P5 (grey) with the alpha channel stripped; the
 // whole image is (re)written from the top each time; final write on destruction.
-// The once-per-second progressive rewrite (render.rs:427-432) degenerates to a
-// single write here because the frame arrives in one buffer.
+// The progressive rewrite follows render.rs:427-432: a buffer arriving at a file sink
+// triggers a rewrite of the whole file when none happened yet or the last one is at
+// least a second old.  With a GPU frame arriving in one buffer that is one write per
+// frame; a caller feeding bands (one per GPU) gets the reference's behaviour.
 class PPMStdoutRGBABufferWriter : public RGBABufferWriter {
   public:
     PPMStdoutRGBABufferWriter(bool write_rgb, FileOrAnyWriter *writer) : out_(writer), rgb_(write_rgb) {}
@@ -130,7 +133,13 @@ class PPMStdoutRGBABufferWriter : public RGBABufferWriter {
         if (!image_) throw Panic("called `Option::unwrap()` on a `None` value");
         image_->set_pixels_from_buffer(buffer);
         dirty_ = true;
-        if (out_->is_file) write_buffer_with_header();  // first flush is immediate (render.rs:427-431)
+        // "Flush full image right away" (render.rs:426-432): at most once per second
+        const auto now = std::chrono::steady_clock::now();
+        if (out_->is_file && (!written_once_ || last_written_at_ + std::chrono::seconds(1) <= now)) {
+            written_once_ = true;
+            last_written_at_ = now;
+            write_buffer_with_header();
+        }
     }
 
   private:
@@ -167,6 +176,65 @@ class PPMStdoutRGBABufferWriter : public RGBABufferWriter {
     bool have_dims_ = false;
     std::unique_ptr<RGBABuffer> image_;
     bool rgb_;
+    bool dirty_ = false;
+    bool written_once_ = false;  // last_written_at: Option<Instant> (render.rs:325)
+    std::chrono::steady_clock::time_point last_written_at_;
+};
+
+// Extension: a sink that writes what the `.tga` extension promises.  Layout as the
+// reference's Go sibling writes it (src/go/gotrace.go:248-280): 18-byte header, image type 2
+// (uncompressed true colour), 24 bits per pixel, BGR, rows bottom-up.  Same seam, same buffering
+// rules as the PPM sink; selected with `--format tga` (the default stays the reference's P6).
+inline void write_tga(FILE *f, uint16_t width, uint16_t height, const uint8_t *px, size_t stride, size_t comps) {
+    uint8_t header[18] = {0};
+    header[2] = 2;
+    header[12] = (uint8_t)(width & 0xff), header[13] = (uint8_t)(width >> 8);
+    header[14] = (uint8_t)(height & 0xff), header[15] = (uint8_t)(height >> 8);
+    header[16] = 24;
+    if (fwrite(header, 1, sizeof(header), f) != sizeof(header)) throw Panic("write_all failed");
+    std::vector<uint8_t> line((size_t)width * 3);
+    for (uint32_t y = height; y-- > 0;) {  // bottom row first
+        const uint8_t *row = px + (size_t)y * stride;
+        for (uint32_t x = 0; x < width; x++) {
+            line[x * 3 + 0] = row[x * comps + 2];
+            line[x * 3 + 1] = row[x * comps + 1];
+            line[x * 3 + 2] = row[x * comps + 0];
+        }
+        if (fwrite(line.data(), 1, line.size(), f) != line.size()) throw Panic("write_all failed");
+    }
+    fflush(f);
+}
+
+class TGARGBABufferWriter : public RGBABufferWriter {
+  public:
+    explicit TGARGBABufferWriter(FileOrAnyWriter *writer) : out_(writer) {}
+    ~TGARGBABufferWriter() override {
+        try {
+            flush();
+        } catch (...) {
+        }
+    }
+    void begin(uint16_t x, uint16_t y) override {
+        width_ = x, height_ = y;
+        ImageRegion r;
+        r.l = 0, r.r = x, r.b = 0, r.t = y;
+        image_.reset(new RGBABuffer(r));
+    }
+    void write_rgba_buffer(const RGBABuffer &buffer) override {
+        if (!image_) throw Panic("called `Option::unwrap()` on a `None` value");
+        image_->set_pixels_from_buffer(buffer);
+        dirty_ = true;
+    }
+
+  private:
+    void flush() {
+        if (!dirty_) return;
+        write_tga(out_->f, width_, height_, image_->buffer(), (size_t)width_ * 4, 4);
+        dirty_ = false;
+    }
+    FileOrAnyWriter *out_;
+    uint16_t width_ = 0, height_ = 0;
+    std::unique_ptr<RGBABuffer> image_;
     bool dirty_ = false;
 };
 

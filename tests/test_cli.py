@@ -105,3 +105,26 @@ def test_sizes_the_reference_rejects_and_extensions(rtrace, tmp_path):
     frames = [(tmp_path / ("s.%04d.tga" % f)).read_bytes() for f in range(3)]
     one = run(rtrace, "--width=64", "--height=64", "-")
     assert frames[0] == one.stdout and frames[1] != frames[0]
+
+
+def test_format_flag_is_validated(rtrace, tmp_path):
+    assert run(rtrace, "--format=bmp", "o.tga", cwd=str(tmp_path)).returncode == 1
+
+
+@pytest.mark.gpu
+def test_real_tga_output_holds_the_same_pixels(rtrace, tmp_path):
+    """--format tga (extension): 18-byte header, 24-bit BGR, bottom-up (gotrace.go:248-280)."""
+    w, h = 96, 64
+    ppm = run(rtrace, "--width=%d" % w, "--height=%d" % h, "--samples-per-pixel=2", "-")
+    r = run(rtrace, "--width=%d" % w, "--height=%d" % h, "--samples-per-pixel=2", "--format=tga", "t.tga", cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr
+    data = (tmp_path / "t.tga").read_bytes()
+    assert len(data) == 18 + w * h * 3
+    assert data[:18] == bytes([0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, w & 255, w >> 8, h & 255, h >> 8, 24, 0])
+    rgb = ppm.stdout[len(b"P6\n96 64\n255\n"):]
+    rows = [rgb[y * w * 3:(y + 1) * w * 3] for y in range(h)]
+    expect = b"".join(bytes(b for x in range(w) for b in (row[3 * x + 2], row[3 * x + 1], row[3 * x])) for row in reversed(rows))
+    assert data[18:] == expect
+    # the sweep path writes the same format
+    r = run(rtrace, "--width=%d" % w, "--height=%d" % h, "--samples-per-pixel=2", "--format=tga", "--frames=2", "s.tga", cwd=str(tmp_path))
+    assert r.returncode == 0 and (tmp_path / "s.0000.tga").read_bytes() == data
