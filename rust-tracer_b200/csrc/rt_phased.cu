@@ -439,8 +439,8 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
     const V3 to_light = vmulf(light, -1.0f);  // render.rs:206
     // render.rs:172-186, :199 -- constants folded at compile time in IEEE f32
     constexpr float OBJ_R = 174.0f / 255.0f, OBJ_G = 49.0f / 255.0f, BG_R = 34.0f / 255.0f, BG_G = 10.0f / 255.0f;
-    const V3 K_object = v3(OBJ_R, OBJ_G, OBJ_G), K_background = v3(BG_R, BG_G, BG_G);
-    const V3 K_ambient = v3(fmul(BG_R, 0.8f), fmul(BG_G, 0.8f), fmul(BG_G, 0.8f));
+    const float AMB_R = fmul(BG_R, 0.8f), AMB_G = fmul(BG_G, 0.8f);  // render.rs:181-186
+    const bool pair_aligned = ((reinterpret_cast<uintptr_t>(p.out) | p.pitch) & 7u) == 0;
     const float sqrt_eps = __uint_as_float(0x39b504f3u);       // sqrt(f32::EPSILON) = 3.4526698e-4
     const float recip = frecip(fmul((float)SPP, (float)SPP));  // render.rs:219-220
 
@@ -456,15 +456,13 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
     __syncthreads();
     if (pt_x >= geo.ptiles_x || pt_y >= geo.ptiles_y) return;  // cull tile on the frame edge
     unsigned n_hits = 0, n_shadow = 0;
-    V3 c = v3(0.0f, 0.0f, 0.0f);  // colour / alpha of the pixel being accumulated (render.rs:233-234)
-    float alpha = 0.0f;
+    float cr = 0.0f, cg = 0.0f, alpha = 0.0f;  // red, green (= blue), alpha of the pixel being accumulated (render.rs:233-234)
     if (tile_hdr.z == 0x7f800000u) {
         // no ray of this cull tile hit anything: every sample adds BACKGROUND (render.rs:190-193)
         if (lane_in) {
-            for (int smp = 0; smp < NS; smp++) c = vadd(c, K_background);
-            const V3 q = vmulf(c, recip);
-            const uint32_t px = scale_u8_fast(q.x) | (scale_u8_fast(q.y) << 8) | (scale_u8_fast(q.z) << 16) |
-                                (scale_u8_fast(fmul(0.0f, recip)) << 24);
+            for (int smp = 0; smp < NS; smp++) cr = fadd(cr, BG_R), cg = fadd(cg, BG_G);
+            const uint32_t g8 = scale_u8_fast(fmul(cg, recip));
+            const uint32_t px = scale_u8_fast(fmul(cr, recip)) | (g8 << 8) | (g8 << 16) | (scale_u8_fast(fmul(0.0f, recip)) << 24);
             for (int pi = 0; pi < G::NPX; pi++) {
                 uint32_t x, j;
                 slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, pi, x, j);
@@ -478,7 +476,6 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
     } else {
         // Every lane takes part (warp-wide ballots below); lanes outside the frame have no hits and store nothing.
         const V3x2 eye2 = v3x2s(eye), light2 = v3x2s(light), to_light2 = v3x2s(to_light);
-        const F2 e1a = f2(p.lframe[0], p.lframe[3]), e1b = f2(p.lframe[1], p.lframe[4]), e1c = f2(p.lframe[2], p.lframe[5]);
         constexpr int GS = 4;  // slots per group: two packed pairs share one candidate pre-filter pass
 #pragma unroll 1
         for (int g0 = 0; g0 < S; g0 += GS) {
@@ -511,8 +508,12 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
                     const F2 gg = vdot2(one, nrm, light2);
                     const V3x2 o = vadd2(one, vadd2(one, eye2, vmulf2(d, dist)), vmulf2(nrm, f2mul(dist, f2s(sqrt_eps))));
                     no[k] = V3x2{f2neg(o.x), f2neg(o.y), f2neg(o.z)};
-                    nuv[k][0] = f2fma(f2s(no[k].x.x), e1a, f2fma(f2s(no[k].y.x), e1b, f2mul(f2s(no[k].z.x), e1c)));
-                    nuv[k][1] = f2fma(f2s(no[k].x.y), e1a, f2fma(f2s(no[k].y.y), e1b, f2mul(f2s(no[k].z.y), e1c)));
+                    {   // -(o . e1) and -(o . e2) for both slots at once, then re-paired per slot
+                        const F2 nu = f2fma(no[k].x, f2s(p.lframe[0]), f2fma(no[k].y, f2s(p.lframe[1]), f2mul(no[k].z, f2s(p.lframe[2]))));
+                        const F2 nv = f2fma(no[k].x, f2s(p.lframe[3]), f2fma(no[k].y, f2s(p.lframe[4]), f2mul(no[k].z, f2s(p.lframe[5]))));
+                        nuv[k][0] = f2(nu.x, nv.x);
+                        nuv[k][1] = f2(nu.y, nv.y);
+                    }
                     g[2 * k] = hit0 ? gg.x : RT_INF;
                     g[2 * k + 1] = hit1 ? gg.y : RT_INF;
                     if (hit0 && !(gg.x >= 0.0f)) pend |= 1u << (2 * k);
@@ -615,46 +616,66 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
                 }
             }
             // ---- C: accumulate in reference sample order (render.rs:236-250), quantise, store (render.rs:92-109) ----
+            // Only red and green are carried: OBJECT, BACKGROUND and AMBIENT_OFFSET have g == b (render.rs:172-186)
+            // and both channels go through the same operations, so blue equals green bit for bit.
+            uint32_t px[GS];
+            bool px_ok[GS];
 #pragma unroll
             for (int i = 0; i < GS; i++) {
                 const int s = g0 + i;
+                px[i] = 0u, px_ok[i] = false;
                 if (s < S) {
                     const int smp = s % NS;
                     const uint32_t x = xs[i], j = js[i];
                     const bool inside = x < p.width && j < p.row_count;
-                    if (smp == 0) {
-                        c = v3(0.0f, 0.0f, 0.0f);
-                        alpha = 0.0f;
-                    }
+                    if (smp == 0) cr = 0.0f, cg = 0.0f, alpha = 0.0f;
                     uint8_t kind;
                     if (g[i] == RT_INF) {  // render.rs:190-193
-                        c = vadd(c, K_background);
+                        cr = fadd(cr, BG_R), cg = fadd(cg, BG_G);
                         kind = K_BACKGROUND;
                     } else if (g[i] >= 0.0f) {  // render.rs:195-198
-                        c = vadd(c, K_ambient);
+                        cr = fadd(cr, AMB_R), cg = fadd(cg, AMB_G);
                         kind = K_AWAY;
                         if (DIAG && inside) n_hits++;
                     } else {
                         if (DIAG && inside) n_hits++, n_shadow++;
                         const float ng = -g[i];
                         if (!((occluded >> i) & 1u)) {  // render.rs:208-210
-                            c = vadd(vadd(c, vmulf(K_object, ng)), K_ambient);
+                            cr = fadd(fadd(cr, fmul(OBJ_R, ng)), AMB_R), cg = fadd(fadd(cg, fmul(OBJ_G, ng)), AMB_G);
                             alpha = fadd(alpha, 1.0f);
                             kind = K_LIT;
                         } else {  // render.rs:211-214
-                            c = vadd(vadd(c, K_background), vmulf(K_ambient, ng));
+                            cr = fadd(fadd(cr, BG_R), fmul(AMB_R, ng)), cg = fadd(fadd(cg, BG_G), fmul(AMB_G, ng));
                             kind = K_SHADOWED;
                         }
                     }
                     if (DIAG && p.kinds && inside) p.kinds[((size_t)j * p.width + x) * NS + smp] = kind;
-                    if (smp == NS - 1 && inside) {
-                        const V3 q = vmulf(c, recip);
-                        const float al = fmul(alpha, recip);
-                        const uint32_t px = scale_u8_fast(q.x) | (scale_u8_fast(q.y) << 8) |
-                                            (scale_u8_fast(q.z) << 16) | (scale_u8_fast(al) << 24);
-                        *reinterpret_cast<uint32_t *>(p.out + (size_t)out_row(p, j) * p.pitch + (size_t)x * 4) = px;
+                    if (smp == NS - 1) {
+                        // render.rs:249-250: * 1/(spp*spp); for one sample that factor is exactly 1.0f and x * 1 == x
+                        const float qr = NS == 1 ? cr : fmul(cr, recip), qg = NS == 1 ? cg : fmul(cg, recip);
+                        const float al = NS == 1 ? alpha : fmul(alpha, recip);
+                        const uint32_t g8 = scale_u8_fast(qg);
+                        px[i] = scale_u8_fast(qr) | (g8 << 8) | (g8 << 16) | (scale_u8_fast(al) << 24);
+                        px_ok[i] = inside;
                     }
                 }
+            }
+            if (NS == 1 && PXW == 2) {
+                // slots 2k, 2k+1 are horizontal neighbours (slot_pixel): one 8-byte store per pair
+#pragma unroll
+                for (int i = 0; i < GS; i += 2) {
+                    uint8_t *at = p.out + (size_t)out_row(p, js[i]) * p.pitch + (size_t)xs[i] * 4;
+                    if (px_ok[i] && px_ok[i + 1] && pair_aligned) {
+                        *reinterpret_cast<uint2 *>(at) = make_uint2(px[i], px[i + 1]);
+                    } else {
+                        if (px_ok[i]) *reinterpret_cast<uint32_t *>(at) = px[i];
+                        if (px_ok[i + 1]) *reinterpret_cast<uint32_t *>(at + 4) = px[i + 1];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < GS; i++)
+                    if (px_ok[i]) *reinterpret_cast<uint32_t *>(p.out + (size_t)out_row(p, js[i]) * p.pitch + (size_t)xs[i] * 4) = px[i];
             }
         }
     }
