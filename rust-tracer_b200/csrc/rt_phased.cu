@@ -114,6 +114,13 @@ RT_DEV float ord2f(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff));
 RT_DEV float warp_min_f(float f) { return ord2f(__reduce_min_sync(FULLMASK, f2ord(f))); }
 RT_DEV float warp_max_f(float f) { return ord2f(__reduce_max_sync(FULLMASK, f2ord(f))); }
 
+// Asynchronous staging of a chunk into shared memory (LDGSTS): the copy is in flight while the warp
+// generates its rays; stage_wait() + __syncthreads() right before the first use.
+RT_DEV void stage_async(uint4 *dst, const uint4 *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+RT_DEV void stage_wait() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
 static constexpr uint32_t PU = 4;  // 16-byte units per primary candidate record
 static constexpr uint32_t SU = 3;  // 16-byte units per shadow candidate record
 
@@ -225,12 +232,18 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
     const bool lane_in = bx < p.width && bj < p.row_count;
     const uint32_t head = p.tile_hdr[ct].x;
     if (head == NO_CHUNK) return;  // no candidate at all: K4 sees an empty hit range and never reads the winners
-    if (head != OVERFLOWED) {      // stage the first chunk (almost always the only one) in shared memory
+    const bool staged = head != OVERFLOWED;
+    if (staged) {  // stage the first chunk (almost always the only one) in shared memory, asynchronously
         const uint32_t units = 1u + PU * __ldg(&p.pool[head]).x;
-        for (uint32_t u = threadIdx.x; u < units; u += blockDim.x) stage[u] = __ldg(&p.pool[head + u]);
+        for (uint32_t u = threadIdx.x; u < units; u += blockDim.x) stage_async(&stage[u], &p.pool[head + u]);
     }
-    __syncthreads();
-    if (pt_x >= geo.ptiles_x || pt_y >= geo.ptiles_y) return;  // cull tile on the frame edge
+    if (pt_x >= geo.ptiles_x || pt_y >= geo.ptiles_y) {  // cull tile on the frame edge: only the block's barrier is left to do
+        if (staged) {
+            stage_wait();
+            __syncthreads();
+        }
+        return;
+    }
     auto fetch = [&](uint32_t base, uint32_t off) { return base == head ? stage[off] : __ldg(&p.pool[base + off]); };
     float tmin = RT_INF, tmax = 0.0f;
 
@@ -279,9 +292,16 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
             }
             return lane_in ? mask : 0u;
         };
-        // mask of the first 32 candidates of the first chunk: reused by every slot pair
-        uint32_t mask0 = 0;
-        if (head != NO_CHUNK) mask0 = chunk_mask(head, 0u, min(stage[0].x, 32u));
+        // One pass covers all of the lane's slots (S <= 4): the staged chunk is awaited after ray generation, so
+        // the copy overlaps it.  With more passes the deferred barrier costs registers (spills under the 64-register
+        // cap), so it is taken up front.
+        constexpr bool LAZY = S <= 4;
+        uint32_t mask0 = 0;  // mask of the first 32 candidates of the first chunk: reused by every slot pair
+        if (!LAZY) {
+            stage_wait();
+            __syncthreads();
+            mask0 = chunk_mask(head, 0u, min(stage[0].x, 32u));
+        }
         // GP packed pairs (two slots each) per pass: every candidate record is loaded once for all of them and
         // the pairs' dependency chains interleave.
         constexpr int GP = (S >= 4) ? 2 : 1;
@@ -299,6 +319,11 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
                 d[k] = slot_dir2<SPP>(one, p, x0, image_row(p, j0), s0 % NS, x1, image_row(p, j1), s1 % NS);
                 bd[k] = f2s(RT_INF);
                 bi[k][0] = bi[k][1] = NO_HIT;
+            }
+            if (LAZY) {  // the only pass: every warp of the block arrives here exactly once
+                stage_wait();
+                __syncthreads();
+                mask0 = chunk_mask(head, 0u, min(stage[0].x, 32u));
             }
             auto test = [&](const uint4 u0, const uint4 u1, const uint4 u2) {
                 V3x2 v;
@@ -449,12 +474,23 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
     const bool lane_in = bx < p.width && bj < p.row_count;
     const uint4 tile_hdr = p.tile_hdr[ct];
     const uint32_t head = tile_hdr.y;
-    if (head < OVERFLOWED) {  // stage the first chunk (almost always the only one) in shared memory
+    constexpr bool LAZY = S <= 4;  // one group per lane: await the staged chunk after phase A (see K2)
+    const bool staged = head < OVERFLOWED;
+    if (staged) {  // stage the first chunk (almost always the only one) in shared memory, asynchronously
         const uint32_t units = 1u + SU * __ldg(&p.pool[head]).x;
-        for (uint32_t u = threadIdx.x; u < units; u += blockDim.x) stage[u] = __ldg(&p.pool[head + u]);
+        for (uint32_t u = threadIdx.x; u < units; u += blockDim.x) {
+            if (LAZY) stage_async(&stage[u], &p.pool[head + u]);
+            else stage[u] = __ldg(&p.pool[head + u]);
+        }
     }
-    __syncthreads();
-    if (pt_x >= geo.ptiles_x || pt_y >= geo.ptiles_y) return;  // cull tile on the frame edge
+    if (!LAZY) __syncthreads();
+    if (pt_x >= geo.ptiles_x || pt_y >= geo.ptiles_y) {  // cull tile on the frame edge: only the block's barrier is left to do
+        if (LAZY && staged) {
+            stage_wait();
+            __syncthreads();
+        }
+        return;
+    }
     unsigned n_hits = 0, n_shadow = 0;
     float cr = 0.0f, cg = 0.0f, alpha = 0.0f;  // red, green (= blue), alpha of the pixel being accumulated (render.rs:233-234)
     if (tile_hdr.z == 0x7f800000u) {
@@ -524,6 +560,10 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
                     g[2 * k] = g[2 * k + 1] = RT_INF;
                     xs[2 * k] = xs[2 * k + 1] = js[2 * k] = js[2 * k + 1] = 0xffffffffu;
                 }
+            }
+            if (LAZY && staged) {  // the only group: every warp of the block arrives here exactly once
+                stage_wait();
+                __syncthreads();
             }
             // ---- B: shadow rays {pos: o, dir: -light} against the tile's candidates (render.rs:202-208) ----
             if (head == OVERFLOWED) {  // per-lane walk, any-hit
