@@ -44,6 +44,7 @@ struct CullShared {
     float4 cand4[T_CAND];
     float2 cand2[T_CAND];
     uint32_t stack[T_STACK];
+    float key[T_CAND];  // primary flush: lower bound of a candidate's hit distance (front-to-back order)
 };
 
 // Geometry shared by the four phases.
@@ -140,21 +141,33 @@ RT_DEV uint32_t flush_reserve(const RenderParams &p, int lane, uint32_t n, uint3
     if (ok && lane == 0) p.pool[base] = make_uint4(n, head, 0u, 0u);
     return base;
 }
-RT_DEV uint32_t flush_primary(const RenderParams &p, const CullShared &sm, int lane, uint32_t n, uint32_t head) {
+RT_DEV uint32_t flush_primary(const RenderParams &p, CullShared &sm, int lane, uint32_t n, uint32_t head) {
     if (n == 0 || head == OVERFLOWED) return head;
     bool ok;
     const uint32_t base = flush_reserve(p, lane, n, PU, head, ok);
     if (!ok) return OVERFLOWED;
+    // Records are written front to back by a lower bound of the hit distance, |v| - r less the f32 slack of
+    // the exact test (its distance differs from the true one by < 1e-5 at these magnitudes): K2 stops a
+    // lane's candidate loop as soon as that bound exceeds the distances the lane already holds.
+    for (uint32_t c = lane; c < n; c += 32)
+        sm.key[c] = fmaf(asqrt(sm.cand4[c].w) - asqrt(sm.cand2[c].x), 0.9999f, -1e-5f);
+    __syncwarp();
     for (uint32_t c = lane; c < n; c += 32) {
+        const float kc = sm.key[c];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < n; j++) {
+            const float kj = sm.key[j];
+            rank += (kj < kc || (kj == kc && j < c)) ? 1u : 0u;
+        }
         const float4 a = sm.cand4[c];
         const float2 e = sm.cand2[c];
         const uint32_t ax = __float_as_uint(a.x), ay = __float_as_uint(a.y), az = __float_as_uint(a.z);
         const uint32_t nvv = __float_as_uint(-a.w), rr = __float_as_uint(e.x);
         const float4 box = screen_box(p, a, e.x);
-        uint4 *rec = p.pool + base + 1u + PU * c;
+        uint4 *rec = p.pool + base + 1u + PU * rank;
         rec[0] = make_uint4(ax, ax, ay, ay);
         rec[1] = make_uint4(az, az, nvv, nvv);
-        rec[2] = make_uint4(rr, rr, __float_as_uint(e.y), 0u);
+        rec[2] = make_uint4(rr, rr, __float_as_uint(e.y), __float_as_uint(kc));
         rec[3] = make_uint4(__float_as_uint(box.x), __float_as_uint(box.y), __float_as_uint(box.z), __float_as_uint(box.w));
     }
     return base;
@@ -341,10 +354,20 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
                     if (dist.y < bd[k].y || (dist.y == bd[k].y && idx < bi[k][1] && bi[k][1] != NO_HIT)) bd[k].y = dist.y, bi[k][1] = idx;
                 }
             };
-            // hot path: the first 32 candidates of the staged chunk, straight from shared memory
+            // farthest distance the lane still has to beat (+inf while one of its slots has no hit)
+            auto held = [&]() {
+                float h = fmaxf(bd[0].x, bd[0].y);
+#pragma unroll
+                for (int k = 1; k < GP; k++) h = fmaxf(h, fmaxf(bd[k].x, bd[k].y));
+                return h;
+            };
+            // hot path: the first 32 candidates of the staged chunk, straight from shared memory; they come
+            // front to back, so the lane is done once a candidate cannot start before what it holds
             for (uint32_t m = mask0; m; m &= m - 1u) {
                 const uint32_t c = (uint32_t)__ffs((int)m) - 1u;
-                test(stage[1u + PU * c], stage[2u + PU * c], stage[3u + PU * c]);
+                const uint4 u2 = stage[3u + PU * c];
+                if (__uint_as_float(u2.w) > held()) break;
+                test(stage[1u + PU * c], stage[2u + PU * c], u2);
             }
             // cold path: the rest of the staged chunk and any further chunks of the chain
             for (uint32_t base = head; base != NO_CHUNK;) {
@@ -353,7 +376,9 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
                 for (uint32_t c0 = (base == head) ? 32u : 0u; c0 < n; c0 += 32) {
                     for (uint32_t m = chunk_mask(base, c0, min(n, c0 + 32u)); m; m &= m - 1u) {
                         const uint32_t c = c0 + (uint32_t)__ffs((int)m) - 1u;
-                        test(fetch(base, 1u + PU * c), fetch(base, 2u + PU * c), fetch(base, 3u + PU * c));
+                        const uint4 u2 = fetch(base, 3u + PU * c);
+                        if (__uint_as_float(u2.w) > held()) break;  // each chunk is sorted front to back
+                        test(fetch(base, 1u + PU * c), fetch(base, 2u + PU * c), u2);
                     }
                 }
                 base = hdr.y;
