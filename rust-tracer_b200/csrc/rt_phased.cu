@@ -30,6 +30,9 @@ namespace rt {
 
 static constexpr uint32_t NO_CHUNK = 0xffffffffu;
 static constexpr uint32_t OVERFLOWED = 0xfffffffeu;
+#ifndef RT_SHADOW_CAP
+#define RT_SHADOW_CAP 768
+#endif
 static constexpr int P_WARPS = 4;  // warps per block in every phase (independent warps)
 // K2 / K4 are latency-bound below ~32 resident warps per SM (ncu: 4 blocks of 100 registers -> 49 %
 // issue-active on C3; capped at 64 registers -> 8 blocks of 4 warps, a few bytes of spill, 1.2x faster).
@@ -458,8 +461,13 @@ __global__ void __launch_bounds__(32 * P_WARPS) phase_cull_shadow(const RenderPa
     cull_begin<false>(p, sm, sb, lane, cs);
     uint32_t head = NO_CHUNK;
     bool done;
+    uint32_t total = 0;
     do {
         done = cull_run<false>(p, sm, sb, lane, cs);
+        total += cs.ncand;
+        // Past a few hundred candidates the list costs more than the per-lane any-hit walk (measured at level 10:
+        // tiles with 1,000-2,800 candidates); such a tile is handed to that walk, as on pool exhaustion.
+        if (total > (uint32_t)RT_SHADOW_CAP) head = OVERFLOWED;
         head = flush_shadow(p, sm, sb, lane, cs.ncand, head);
         __syncwarp();
     } while (!done && head != OVERFLOWED);
