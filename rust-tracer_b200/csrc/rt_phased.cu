@@ -23,6 +23,8 @@
 // A cull tile whose candidates do not fit the pool is flagged and its pixel tiles
 // fall back to the per-lane walk (lane_traverse): the output never depends on the
 // pool size.  Exactness argument: see rt_tile.cu.
+#include <type_traits>
+
 #include "rt_pack.cuh"
 #include "rt_kernels.h"
 
@@ -577,12 +579,11 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
                     const F2 gg = vdot2(one, nrm, light2);
                     const V3x2 o = vadd2(one, vadd2(one, eye2, vmulf2(d, dist)), vmulf2(nrm, f2mul(dist, f2s(sqrt_eps))));
                     no[k] = V3x2{f2neg(o.x), f2neg(o.y), f2neg(o.z)};
-                    {   // -(o . e1) and -(o . e2) for both slots at once, then re-paired per slot
-                        const F2 nu = f2fma(no[k].x, f2s(p.lframe[0]), f2fma(no[k].y, f2s(p.lframe[1]), f2mul(no[k].z, f2s(p.lframe[2]))));
-                        const F2 nv = f2fma(no[k].x, f2s(p.lframe[3]), f2fma(no[k].y, f2s(p.lframe[4]), f2mul(no[k].z, f2s(p.lframe[5]))));
-                        nuv[k][0] = f2(nu.x, nv.x);
-                        nuv[k][1] = f2(nu.y, nv.y);
-                    }
+                    // -(o . e1, o . e2) per slot, computed straight into the pair the pre-filter adds to a candidate
+                    nuv[k][0] = f2(fmaf(no[k].x.x, p.lframe[0], fmaf(no[k].y.x, p.lframe[1], no[k].z.x * p.lframe[2])),
+                                   fmaf(no[k].x.x, p.lframe[3], fmaf(no[k].y.x, p.lframe[4], no[k].z.x * p.lframe[5])));
+                    nuv[k][1] = f2(fmaf(no[k].x.y, p.lframe[0], fmaf(no[k].y.y, p.lframe[1], no[k].z.y * p.lframe[2])),
+                                   fmaf(no[k].x.y, p.lframe[3], fmaf(no[k].y.y, p.lframe[4], no[k].z.y * p.lframe[5])));
                     g[2 * k] = hit0 ? gg.x : RT_INF;
                     g[2 * k + 1] = hit1 ? gg.y : RT_INF;
                     if (hit0 && !(gg.x >= 0.0f)) pend |= 1u << (2 * k);
@@ -644,11 +645,11 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
                     }
                 }
                 ulo = warp_min_f(ulo), uhi = warp_max_f(uhi), vlo = warp_min_f(vlo), vhi = warp_max_f(vhi);
-                const uint32_t first = head;
-                for (uint32_t base = first; base != NO_CHUNK;) {
-                    const bool staged = base == first;
-                    const uint4 hdr = staged ? stage[0] : __ldg(&p.pool[base]);
-                    auto unit = [&](uint32_t off) { return staged ? stage[off] : __ldg(&p.pool[base + off]); };
+                // one chunk of the tile's chain: STAGED = the first one, read from shared memory
+                auto run_chunk = [&](auto staged_tag, uint32_t base) -> uint32_t {
+                    constexpr bool STAGED = decltype(staged_tag)::value;
+                    auto unit = [&](uint32_t off) { return STAGED ? stage[off] : __ldg(&p.pool[base + off]); };
+                    const uint4 hdr = unit(0u);
                     for (uint32_t c0 = 0; c0 < hdr.x; c0 += 32) {
                         // warp level: lane tests candidate c0 + lane (disc vs rectangle)
                         bool w_ok = false;
@@ -684,9 +685,10 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
                             shadow_test(1, u0, u1);
                         }
                     }
-                    base = hdr.y;
-                    if (__ballot_sync(FULLMASK, pend != 0u) == 0u) break;
-                }
+                    return hdr.y;
+                };
+                uint32_t next = run_chunk(std::true_type{}, head);
+                while (next != NO_CHUNK && __ballot_sync(FULLMASK, pend != 0u) != 0u) next = run_chunk(std::false_type{}, next);
             }
             // ---- C: accumulate in reference sample order (render.rs:236-250), quantise, store (render.rs:92-109) ----
             // Only red and green are carried: OBJECT, BACKGROUND and AMBIENT_OFFSET have g == b (render.rs:172-186)
@@ -728,7 +730,9 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
                         const float qr = NS == 1 ? cr : fmul(cr, recip), qg = NS == 1 ? cg : fmul(cg, recip);
                         const float al = NS == 1 ? alpha : fmul(alpha, recip);
                         const uint32_t g8 = scale_u8_fast(qg);
-                        px[i] = scale_u8_fast(qr) | (g8 << 8) | (g8 << 16) | (scale_u8_fast(al) << 24);
+                        // one sample: alpha is exactly 0 or 1, and trunc(0.5 + 255 * 1) = 255
+                        const uint32_t a8 = NS == 1 ? (al != 0.0f ? 255u : 0u) : scale_u8_fast(al);
+                        px[i] = scale_u8_fast(qr) | (g8 << 8) | (g8 << 16) | (a8 << 24);
                         px_ok[i] = inside;
                     }
                 }
