@@ -108,6 +108,27 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(rows), "reasons": reasons}
 
 
+def pin_to_gpu_cpus(local_rank):
+    """Multi-GPU runs: keep this rank's host threads (and so its pinned frame buffers, first touch) on the
+    CPUs NVML reports as local to its GPU, so that eight ranks copying frames out do not cross sockets."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local_rank]) if vis and vis.split(",")[local_rank].isdigit() else local_rank
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "%d cpus local to GPU %d" % (len(cpus), idx)
+    except Exception as e:   # best effort
+        return "not pinned (%s)" % type(e).__name__
+    return "not pinned"
+
+
 def cpu_leg(width, height, spp, level, min_seconds, row_stride):
     """The oracle (CPU restatement of the reference algorithm) on every host core."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -200,6 +221,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cpu_note = pin_to_gpu_cpus(local_rank) if world > 1 and not os.environ.get("RTRACE_NO_PIN") else None
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this benchmark has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local_rank)
@@ -381,7 +403,7 @@ def main():
                 "l2": "not flushed" if flush is None else "flushed between steps (256 MiB memset, outside the timed events)",
                 "rays_per_frame": {"primary": primary * (world if bands else 1), "shadow": None if bands else shadow},
                 "mpixels_per_s": width * height * (1 if bands else world) / (ms_per_step * 1e-3) / 1e6,
-                "variant": args.variant, "wall_ms_per_step_incl_flush": wall_ms / args.steps,
+                "variant": args.variant, "wall_ms_per_step_incl_flush": wall_ms / args.steps, "host_cpus": cpu_note,
             },
             "roofline": {
                 "bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
