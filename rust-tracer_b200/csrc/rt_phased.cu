@@ -7,22 +7,32 @@
 // kind of work at full occupancy; intermediates are a few MB and stay in L2:
 //
 //   K1 cull_primary   one warp per CULL tile (CW x CH pixel tiles): walks the
-//                     skip-pointer hierarchy against the tile's cone, appends
-//                     candidate chunks {v = c - eye, v.v, r*r, index} to a pool.
-//   K2 test_primary   one warp per PIXEL tile: lane pre-filter + the reference's
-//                     exact f32 ray-sphere test (primitive.rs:55-72) over the
-//                     tile's candidates; writes the winner index per sample and
-//                     the tile's hit-distance range (atomicMin/Max).
+//                     skip-pointer hierarchy against the tile's cone, dropping what
+//                     lies wholly behind a leaf that every ray of the tile hits
+//                     (primary_occlusion); appends candidate chunks {v = c - eye,
+//                     v.v, r*r, index, image-space box}, sorted front to back.
+//   K2 test_primary   one warp per PIXEL tile: box pre-filter (warp rectangle, then
+//                     the lane's own pixel block) + the reference's exact f32
+//                     ray-sphere test (primitive.rs:55-72) over the survivors, until
+//                     the next candidate cannot start before what the lane holds;
+//                     writes the winner index per sample and the tile's
+//                     hit-distance range (atomicMin/Max).
 //   K3 cull_shadow    one warp per cull tile: shadow beam from that range, walk,
-//                     append shadow candidate chunks {c, r*r}.
+//                     append shadow candidate chunks {c, r*r, disc in the plane
+//                     perpendicular to the light}; a leaf that occludes every shadow
+//                     ray of the tile ends the walk (shadow_cover).
 //   K4 shade_store    one warp per pixel tile: winner distance, normal, g, shadow
-//                     origin (render.rs:194-199), exact any-hit tests
-//                     (render.rs:202-208), accumulation in reference sample order,
-//                     RGBA8 quantisation, one framebuffer store per pixel.
+//                     origin (render.rs:194-199), disc pre-filter (warp rectangle,
+//                     then per slot) + exact any-hit tests (render.rs:202-208),
+//                     accumulation in reference sample order, RGBA8 quantisation,
+//                     one framebuffer store per pixel (pair).
 //
-// A cull tile whose candidates do not fit the pool is flagged and its pixel tiles
-// fall back to the per-lane walk (lane_traverse): the output never depends on the
-// pool size.  Exactness argument: see rt_tile.cu.
+// Every pre-filter keeps a superset of what the exact test can accept (the worst-case
+// f32 error of the discriminant is folded into the radii); the exact tests are the
+// reference's operations one by one, so the bytes are the oracle's.  A cull tile whose
+// candidates do not fit the pool (or whose shadow list passes RT_SHADOW_CAP) is flagged
+// and its pixel tiles fall back to the per-lane walk (lane_traverse): the output never
+// depends on the pool size.  Exactness argument: see rt_tile.cu and DESIGN.md section 4.
 #include <type_traits>
 
 #include "rt_pack.cuh"
@@ -32,6 +42,8 @@ namespace rt {
 
 static constexpr uint32_t NO_CHUNK = 0xffffffffu;
 static constexpr uint32_t OVERFLOWED = 0xfffffffeu;
+// Shadow candidates per tile beyond which the per-lane any-hit walk is cheaper than the list (measured:
+// level 10 tiles with 1,000-2,800 candidates; 384 sends too many supersampled tiles to the walk, 1536 too few).
 #ifndef RT_SHADOW_CAP
 #define RT_SHADOW_CAP 768
 #endif
