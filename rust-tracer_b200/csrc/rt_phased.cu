@@ -249,8 +249,8 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const G geo(p.width, p.row_count);
     // one block per cull tile, one warp per pixel tile of it
-    const uint32_t ct = blockIdx.x;
-    const uint32_t pt_x = (ct % geo.ctiles_x) * CW + (uint32_t)(warp % CW), pt_y = (ct / geo.ctiles_x) * CH + (uint32_t)(warp / CW);
+    const uint32_t ct = blockIdx.y * geo.ctiles_x + blockIdx.x;  // 2-D grid of cull tiles: no division
+    const uint32_t pt_x = blockIdx.x * CW + (uint32_t)(warp % CW), pt_y = blockIdx.y * CH + (uint32_t)(warp / CW);
     const uint32_t pt = pt_y * geo.ptiles_x + pt_x;
     const uint32_t tile_x0 = pt_x * G::TW, tile_j0 = pt_y * G::TH;
     const V3 eye = v3(p.eye[0], p.eye[1], p.eye[2]);
@@ -499,8 +499,8 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const G geo(p.width, p.row_count);
     // one block per cull tile, one warp per pixel tile of it
-    const uint32_t ct = blockIdx.x;
-    const uint32_t pt_x = (ct % geo.ctiles_x) * CW + (uint32_t)(warp % CW), pt_y = (ct / geo.ctiles_x) * CH + (uint32_t)(warp / CW);
+    const uint32_t ct = blockIdx.y * geo.ctiles_x + blockIdx.x;  // 2-D grid of cull tiles: no division
+    const uint32_t pt_x = blockIdx.x * CW + (uint32_t)(warp % CW), pt_y = blockIdx.y * CH + (uint32_t)(warp / CW);
     const uint32_t pt = pt_y * geo.ptiles_x + pt_x;
     const uint32_t tile_x0 = pt_x * G::TW, tile_j0 = pt_y * G::TH;
     const uint32_t *winner = p.winner + (size_t)pt * S * 32;
@@ -791,13 +791,14 @@ static cudaError_t launch_phased(bool diag, const RenderParams &p, cudaStream_t 
     cudaError_t e = cudaMemsetAsync(p.pool_count, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
     const unsigned cb = (nc + P_WARPS - 1) / P_WARPS;
+    const dim3 tiles2d(geo.ctiles_x, geo.ctiles_y);  // K2 / K4: one block per cull tile
     phase_cull_primary<SPP, PXW, PXH, CW, CH><<<cb, 32 * P_WARPS, 0, stream>>>(p);
-    phase_test_primary<SPP, PXW, PXH, CW, CH><<<nc, 32 * CW * CH, 0, stream>>>(p);
+    phase_test_primary<SPP, PXW, PXH, CW, CH><<<tiles2d, 32 * CW * CH, 0, stream>>>(p);
     phase_cull_shadow<SPP, PXW, PXH, CW, CH><<<cb, 32 * P_WARPS, 0, stream>>>(p);
     if (diag)
-        phase_shade_store<SPP, PXW, PXH, CW, CH, true><<<nc, 32 * CW * CH, 0, stream>>>(p);
+        phase_shade_store<SPP, PXW, PXH, CW, CH, true><<<tiles2d, 32 * CW * CH, 0, stream>>>(p);
     else
-        phase_shade_store<SPP, PXW, PXH, CW, CH, false><<<nc, 32 * CW * CH, 0, stream>>>(p);
+        phase_shade_store<SPP, PXW, PXH, CW, CH, false><<<tiles2d, 32 * CW * CH, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
