@@ -345,3 +345,25 @@ def test_phased_prefilters_hold_for_cameras_and_lights(rt, oracle, kw, frames):
             assert_same(img, ref, "%s orbit frame %d spp %d" % (kw, f, spp))
     finally:
         rt.set_variant(rt.VARIANT_AUTO)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(eye=(0.3, 0.6, -3.4)),                                          # just outside the root bound: many tiles fully covered
+    dict(origin=(0.0, -2.0, 4.0), radius=2.5, eye=(0.0, 0.0, -6.0)),     # a scene 2.5x as large
+    dict(eye=(3.0, 1.5, -9.0)),                                          # far and off axis: small projected leaves
+    dict(light=(1.0, -0.4, 3.0)),                                        # light from behind the camera: almost everything lit
+])
+def test_phased_occlusion_culling_holds_for_other_eyes(rt, oracle, kw):
+    """The occlusion pruning of the primary cull and the single-occluder shortcut of the shadow cull
+    assume nothing about Scene::default: other eyes, scene sizes and lights give the oracle's bytes.
+    (Every eye here lies outside the root bound, so the candidate-list kernels really run.)"""
+    w, h, spp, level = 1600, 900, 1, 8
+    gs, os_ = rt.Scene(level=level, **kw), oracle.Scene(level=level, **kw)
+    ref, _ = os_.render(w, h, spp)
+    rt.set_variant(rt.VARIANT_PHASED)
+    try:
+        assert_same(rt.Renderer.render(rt.RenderOptions(w, h, spp), gs), ref, str(kw))
+        tiles = rt.debug_phased_tiles(gs)
+        assert tiles.shape[1] == 2 and int(tiles[:, 0][tiles[:, 0] != 0xffffffff].sum()) > 0
+    finally:
+        rt.set_variant(rt.VARIANT_AUTO)
