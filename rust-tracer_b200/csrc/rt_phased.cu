@@ -163,11 +163,15 @@ RT_DEV uint32_t flush_primary(const RenderParams &p, CullShared &sm, int lane, u
     bool ok;
     const uint32_t base = flush_reserve(p, lane, n, PU, head, ok);
     if (!ok) return OVERFLOWED;
-    // Records are written front to back by a lower bound of the hit distance, |v| - r less the f32 slack of
-    // the exact test (its distance differs from the true one by < 1e-5 at these magnitudes): K2 stops a
-    // lane's candidate loop as soon as that bound exceeds the distances the lane already holds.
-    for (uint32_t c = lane; c < n; c += 32)
-        sm.key[c] = fmaf(asqrt(sm.cand4[c].w) - asqrt(sm.cand2[c].x), 0.9999f, -1e-5f);
+    // Records are written front to back by a lower bound of the distance the exact test can return.  With
+    // disc_f32 <= disc + eps (eps = EPS_DISC (v.v + r*r), rt_cull.cuh) the f32 root b - sqrt(disc_f32) is smallest
+    // head-on, where it is |v| - sqrt(r*r + eps): the inflated radius of the cull, not r (for the smallest leaves
+    // the two differ by ~1e-3).  K2 stops a lane's candidate loop as soon as that bound exceeds the distances
+    // the lane already holds.
+    for (uint32_t c = lane; c < n; c += 32) {
+        const float vv = sm.cand4[c].w, rr = sm.cand2[c].x;
+        sm.key[c] = fmaf(asqrt(vv) - asqrt(fmaf(EPS_DISC, vv + rr, rr)), 0.99999f, -1e-5f);
+    }
     __syncwarp();
     for (uint32_t c = lane; c < n; c += 32) {
         const float kc = sm.key[c];
