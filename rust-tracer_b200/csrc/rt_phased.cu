@@ -47,7 +47,10 @@ static constexpr uint32_t OVERFLOWED = 0xfffffffeu;
 #ifndef RT_SHADOW_CAP
 #define RT_SHADOW_CAP 768
 #endif
-static constexpr int P_WARPS = 4;  // warps per block in every phase (independent warps)
+#ifndef RT_P_WARPS
+#define RT_P_WARPS 4
+#endif
+static constexpr int P_WARPS = RT_P_WARPS;  // warps per block of the cull launches (independent warps)
 // K2 / K4 are latency-bound below ~32 resident warps per SM (ncu: 4 blocks of 100 registers -> 49 %
 // issue-active on C3; capped at 64 registers -> 8 blocks of 4 warps, a few bytes of spill, 1.2x faster).
 #ifndef RT_PHASED_WARPS_PER_SM
@@ -259,7 +262,14 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
     const uint32_t tile_x0 = pt_x * G::TW, tile_j0 = pt_y * G::TH;
     const V3 eye = v3(p.eye[0], p.eye[1], p.eye[2]);
     const ONE2 one = f2s(p.one);  // 1.0f the compiler cannot see (rt_pack.cuh)
-    uint32_t *winner = p.winner + (size_t)pt * S * 32;
+    // one sample per pixel: the winner's distance travels with its index (8 bytes per sample, still L2-resident at 4K);
+    // supersampled frames keep 4 bytes per sample (their winners stream through HBM) and K4 recomputes the distance
+    constexpr bool WDIST = NS == 1;
+    uint32_t *winner = p.winner + (size_t)pt * S * 32 * (WDIST ? 2 : 1);
+    auto put_winner = [&](int s, uint32_t idx, float dist) {
+        if (WDIST) reinterpret_cast<uint2 *>(winner)[s * 32 + lane] = make_uint2(idx, __float_as_uint(dist));
+        else winner[s * 32 + lane] = idx;
+    };
 
     uint32_t bx, bj;  // first pixel of this lane's block
     slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, 0, bx, bj);
@@ -286,14 +296,14 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
             uint32_t x, j;
             slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s / NS, x, j);
             uint32_t bi = NO_HIT;
+            float hitd = RT_INF;
             if (x < p.width && j < p.row_count) {
                 const V3 d = slot_dir<SPP>(p, x, image_row(p, j), s % NS);
-                float hitd = RT_INF;
                 lane_traverse<false>(p.sph, p.skip, p.n_nodes, eye, d, hitd, bi);
                 if (hitd == RT_INF) bi = NO_HIT;
                 else tmin = fminf(tmin, fabsf(hitd)), tmax = fmaxf(tmax, fabsf(hitd));
             }
-            winner[s * 32 + lane] = bi;
+            put_winner(s, bi, hitd);
         }
     } else {
         // Sample-coordinate rectangles of this lane's own block and of the warp's pixel tile: a
@@ -408,11 +418,11 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
             for (int k = 0; k < GP; k++) {
                 const int s0 = g0 + 2 * k, s1 = s0 + 1;
                 if (s0 < S) {
-                    winner[s0 * 32 + lane] = bi[k][0];
+                    put_winner(s0, bi[k][0], bd[k].x);
                     if (bi[k][0] != NO_HIT) tmin = fminf(tmin, fabsf(bd[k].x)), tmax = fmaxf(tmax, fabsf(bd[k].x));
                 }
                 if (s1 < S) {
-                    winner[s1 * 32 + lane] = bi[k][1];
+                    put_winner(s1, bi[k][1], bd[k].y);
                     if (bi[k][1] != NO_HIT) tmin = fminf(tmin, fabsf(bd[k].y)), tmax = fmaxf(tmax, fabsf(bd[k].y));
                 }
             }
@@ -507,7 +517,8 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
     const uint32_t pt_x = blockIdx.x * CW + (uint32_t)(warp % CW), pt_y = blockIdx.y * CH + (uint32_t)(warp / CW);
     const uint32_t pt = pt_y * geo.ptiles_x + pt_x;
     const uint32_t tile_x0 = pt_x * G::TW, tile_j0 = pt_y * G::TH;
-    const uint32_t *winner = p.winner + (size_t)pt * S * 32;
+    constexpr bool WDIST = NS == 1;  // K2 stored the winner's distance next to its index
+    const uint32_t *winner = p.winner + (size_t)pt * S * 32 * (WDIST ? 2 : 1);
     const ONE2 one = f2s(p.one);  // 1.0f the compiler cannot see (rt_pack.cuh)
 
     const V3 eye = v3(p.eye[0], p.eye[1], p.eye[2]);
@@ -580,14 +591,22 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
                     slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s1 / NS, xs[2 * k + 1], js[2 * k + 1]);
                     const V3x2 d = slot_dir2<SPP>(one, p, xs[2 * k], image_row(p, js[2 * k]), s0 % NS, xs[2 * k + 1],
                                                   image_row(p, js[2 * k + 1]), s1 % NS);
-                    const uint32_t wi0 = winner[s0 * 32 + lane], wi1 = winner[s1 * 32 + lane];
+                    uint32_t wi0, wi1;
+                    F2 dist;
+                    if (WDIST) {
+                        const uint2 a = reinterpret_cast<const uint2 *>(winner)[s0 * 32 + lane], b = reinterpret_cast<const uint2 *>(winner)[s1 * 32 + lane];
+                        wi0 = a.x, wi1 = b.x, dist = f2(__uint_as_float(a.y), __uint_as_float(b.y));
+                    } else {
+                        wi0 = winner[s0 * 32 + lane], wi1 = winner[s1 * 32 + lane];
+                    }
                     const bool hit0 = wi0 != NO_HIT, hit1 = wi1 != NO_HIT;
                     const float4 w0 = __ldg(&p.sph[hit0 ? wi0 : 0u]), w1 = __ldg(&p.sph[hit1 ? wi1 : 0u]);
                     const V3x2 cen = V3x2{f2(w0.x, w1.x), f2(w0.y, w1.y), f2(w0.z, w1.z)};
-                    const F2 rad = f2(w0.w, w1.w);
-                    // the winner's distance again (primitive.rs:55-72), exactly as K2 computed it
-                    const V3x2 v = vsub2(one, cen, eye2);
-                    F2 dist = primary_distance2(one, v, f2neg(vdot2(one, v, v)), f2mul(rad, rad), d);
+                    if (!WDIST) {  // the winner's distance again (primitive.rs:55-72), exactly as K2 computed it
+                        const F2 rad = f2(w0.w, w1.w);
+                        const V3x2 v = vsub2(one, cen, eye2);
+                        dist = primary_distance2(one, v, f2neg(vdot2(one, v, v)), f2mul(rad, rad), d);
+                    }
                     if (!hit0) dist.x = 1.0f;
                     if (!hit1) dist.y = 1.0f;
                     // primitive.rs:83 normal; render.rs:194 g; render.rs:199 shadow origin
@@ -832,7 +851,7 @@ void rt_phased_scratch(uint32_t width, uint32_t rows, uint32_t spp, int shape, s
             break;
     }
 #undef RT_GEO
-    *winner_bytes = (size_t)np * S * 32 * sizeof(uint32_t);
+    *winner_bytes = (size_t)np * S * 32 * sizeof(uint32_t) * (spp == 1 ? 2 : 1);  // spp 1: {index, distance} per sample
     *hdr_bytes = (size_t)nc * sizeof(uint4);
     uint64_t units = (uint64_t)nc * 384u;
     if (units < (1u << 20)) units = 1u << 20;
