@@ -1,0 +1,44 @@
+"""bench.py's reference arm (`--impl reference`): the CPU restatement of the reference algorithm on the
+host's cores, printed as one JSON line with the keys the driver reads.  Needs no GPU."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run_bench(*args, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + list(args), capture_output=True, text=True,
+                       env=e, timeout=300)
+    return r
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    r = run_bench("--impl", "reference", "--workload", "c1", "--steps", "1", "--warmup", "0")
+    assert r.returncode == 0, r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"].startswith("Mrays/s") and d["unit"] == "Mrays/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "1024x768" in d["config"]["workload"]
+
+
+def test_reference_arm_runs_on_rank_zero_only():
+    r = run_bench("--impl", "reference", "--workload", "c1", "--steps", "1", "--gpus", "2",
+                  env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_native_arm_refuses_to_run_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a GPU is present")
+    r = run_bench("--steps", "1", "--warmup", "3", "--no-cpu-baseline")
+    assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
