@@ -223,16 +223,25 @@ RT_DEV uint32_t flush_shadow(const RenderParams &p, const CullShared &sm, const 
 // ---------------------------------------------------------------------------
 // K1: primary cull, one warp per cull tile
 // ---------------------------------------------------------------------------
-template <int SPP, int PXW, int PXH, int CW, int CH>
+// The primary cull can run on tiles K1C x K1C cull tiles large: the K1C x K1C cull tiles under one walk
+// share its chain (each of their headers gets the same head).  Measured on B200: with 2 x 2 the 8K / 4x4
+// frame (259,200 cull tiles) gains 3.5 % -- a quarter of the walks, each only a little longer -- while 4K
+// frames lose 4-10 % (longer lists for K2 to filter, weaker occlusion pruning), so launch_phased picks
+// K1C = 2 only above 150,000 cull tiles.  The shadow cull always keeps the small tiles: its beams need the
+// tight depth range.
+template <int SPP, int PXW, int PXH, int CW, int CH, int K1C>
 __global__ void __launch_bounds__(32 * P_WARPS) phase_cull_primary(const RenderParams p) {
-    using G = Geo<SPP, PXW, PXH, CW, CH>;
+    using G = Geo<SPP, PXW, PXH, CW, CH>;                   // the cull tiles K2-K4 work on
+    using GC = Geo<SPP, PXW, PXH, CW * K1C, CH * K1C>;      // the tiles this launch walks for
     __shared__ CullShared shared[P_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const G geo(p.width, p.row_count);
-    const uint32_t ct = blockIdx.x * P_WARPS + warp;
-    if (ct >= geo.n_ctiles()) return;
+    const GC geoc(p.width, p.row_count);
+    const uint32_t cc = blockIdx.x * P_WARPS + warp;
+    if (cc >= geoc.n_ctiles()) return;
     CullShared &sm = shared[warp];
-    const PrimaryBeam pb = cull_tile_beam<G>(p, ct % geo.ctiles_x, ct / geo.ctiles_x);
+    const uint32_t ccx = cc % geoc.ctiles_x, ccy = cc / geoc.ctiles_x;
+    const PrimaryBeam pb = cull_tile_beam<GC>(p, ccx, ccy);
     CullState cs;
     cull_begin<true>(p, sm, pb, lane, cs);
     uint32_t head = NO_CHUNK;
@@ -242,7 +251,10 @@ __global__ void __launch_bounds__(32 * P_WARPS) phase_cull_primary(const RenderP
         head = flush_primary(p, sm, lane, cs.ncand, head);
         __syncwarp();
     } while (!done && head != OVERFLOWED);
-    if (lane == 0) p.tile_hdr[ct] = make_uint4(head, NO_CHUNK, 0x7f800000u, 0u);
+    if (lane < K1C * K1C) {
+        const uint32_t fx = ccx * K1C + (uint32_t)(lane % K1C), fy = ccy * K1C + (uint32_t)(lane / K1C);
+        if (fx < geo.ctiles_x && fy < geo.ctiles_y) p.tile_hdr[fy * geo.ctiles_x + fx] = make_uint4(head, NO_CHUNK, 0x7f800000u, 0u);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -815,7 +827,12 @@ static cudaError_t launch_phased(bool diag, const RenderParams &p, cudaStream_t 
     if (e != cudaSuccess) return e;
     const unsigned cb = (nc + P_WARPS - 1) / P_WARPS;
     const dim3 tiles2d(geo.ctiles_x, geo.ctiles_y);  // K2 / K4: one block per cull tile
-    phase_cull_primary<SPP, PXW, PXH, CW, CH><<<cb, 32 * P_WARPS, 0, stream>>>(p);
+    if (nc > 150000u) {
+        const Geo<SPP, PXW, PXH, CW * 2, CH * 2> geoc(p.width, p.row_count);
+        phase_cull_primary<SPP, PXW, PXH, CW, CH, 2><<<(geoc.n_ctiles() + P_WARPS - 1) / P_WARPS, 32 * P_WARPS, 0, stream>>>(p);
+    } else {
+        phase_cull_primary<SPP, PXW, PXH, CW, CH, 1><<<cb, 32 * P_WARPS, 0, stream>>>(p);
+    }
     phase_test_primary<SPP, PXW, PXH, CW, CH><<<tiles2d, 32 * CW * CH, 0, stream>>>(p);
     phase_cull_shadow<SPP, PXW, PXH, CW, CH><<<cb, 32 * P_WARPS, 0, stream>>>(p);
     if (diag)
