@@ -11,7 +11,9 @@ scene (level 8, 21,845 spheres) at 3840x2160, 1 sample per pixel.  With N>1 ever
 rank renders whole frames of that workload (frame-sharded sweep, BASELINE C5's
 partition): no data-path collective, weak scaling.  `--mode bands` instead splits ONE
 frame into interleaved row bands gathered to rank 0 over NCCL (BASELINE C4's
-partition, strong scaling).
+partition, strong scaling).  `--workload c5` is BASELINE configs[4] itself: the 120-frame
+orbit of the camera about the flake over the level-9 scene at 3840x2160, 4x4 samples,
+step i of rank r rendering frame (i*N + r) mod 120 (c1/c3/c4 select the other configs).
 
 metric  = Mrays/s (primary + shadow rays, counted as the reference's work is counted)
 value   = whole-job rays / device time of the K steps (CUDA events on the launch
@@ -39,11 +41,34 @@ WORKLOADS = {
     "c3": (3840, 2160, 4, 9),    # deeper flake (87,381 spheres), 4x4 supersampling
     "c3l10": (3840, 2160, 4, 10),
     "c4": (7680, 4320, 4, 9),
+    "c5": (3840, 2160, 4, 9),    # BASELINE configs[4]: 120-frame orbit sweep of C3-sized frames, frame f -> rank f mod N
 }
+ORBIT_FRAMES = 120               # c5: eye and camera basis rotated about the flake's axis by 2 pi f / 120
 # algorithmic flop per ray of REFERENCE work (17 T + 3 P + 19 U + 20 f_p + 30 f_s),
 # from the oracle's counters (tests/golden/oracle_derived.json); used when the fixture lacks the config.
 FLOP_PER_RAY_FALLBACK = 645.0
 METRIC = "Mrays/s (primary+shadow)"
+
+
+def orbit_basis(frame, n_frames=ORBIT_FRAMES, eye=(0.0, 0.0, -4.0)):
+    """(eye, right, up, forward) of orbit frame `frame`: the reference camera (render.rs:145-166, 238-243)
+    rotated about the vertical axis; frame 0 is the reference camera exactly.  Same arithmetic as
+    rtrace_b200.orbit_camera and the CLI's --frames (host/main.cpp)."""
+    import math
+    th = 2.0 * math.pi * frame / n_frames
+    c, s = (1.0, 0.0) if frame % n_frames == 0 else (math.cos(th), math.sin(th))
+
+    def rot(v):
+        return (c * v[0] + s * v[2], v[1], -s * v[0] + c * v[2])
+    return rot(eye), rot((1, 0, 0)), (0, 1, 0), rot((0, 0, 1))
+
+
+def workload_name(name, level, width, height, spp):
+    s = "%s: pyramid level %d (%d spheres) at %dx%d, %d spp" % (name, level, (4 ** level - 1) // 3, width, height,
+                                                               spp * spp)
+    if name == "c5":
+        s += ", %d-frame orbit sweep (step i on rank r = frame (i*N + r) mod %d)" % (ORBIT_FRAMES, ORBIT_FRAMES)
+    return s
 
 
 def log(*a):
@@ -168,8 +193,11 @@ def run_reference(args, width, height, spp, level):
     t0 = time.perf_counter()
     budget_steps = args.steps
     done = 0
-    for _ in range(budget_steps):
-        _, ctr = s.render_rows(width, height, spp, 0, stride, rows, threads=cores)
+    for i in range(budget_steps):
+        cam = None
+        if args.workload == "c5":   # orbit sweep: step i is frame i of the orbit (same cameras as the native arm)
+            cam = o.make_camera(*orbit_basis(i % ORBIT_FRAMES))
+        _, ctr = s.render_rows(width, height, spp, 0, stride, rows, threads=cores, camera=cam)
         rays += ctr.primary_rays + ctr.shadow_rays
         done += 1
         if time.perf_counter() - t0 > 150.0:   # keep the whole run within a few minutes
@@ -181,8 +209,7 @@ def run_reference(args, width, height, spp, level):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": done,
         "warmup": min(args.warmup, 1), "ms_per_step": secs / done * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: pyramid level %d (%d spheres) at %dx%d, %d spp" % (
-            args.workload, level, (4 ** level - 1) // 3, width, height, spp * spp)},
+        "config": {"workload": workload_name(args.workload, level, width, height, spp)},
         "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -234,6 +261,13 @@ def main():
     opts = rt.RenderOptions(width, height, spp)
     stream = torch.cuda.current_stream()
     bands = args.mode == "bands" and world > 1
+    sweep = args.workload == "c5"
+    if sweep and bands:
+        raise SystemExit("bench.py: c5 is the frame-sharded orbit sweep; use --mode frames")
+    cams = [rt.make_camera(*orbit_basis(f)) for f in range(ORBIT_FRAMES)] if sweep else None
+
+    def frame_of(i):   # c5: step i of this rank renders orbit frame (i * world + rank) mod 120
+        return (i * world + rank) % ORBIT_FRAMES
     from rtrace_b200 import partition
     if bands:
         row_start, row_stride, my_rows = partition.band_spec(height, rank, world)
@@ -269,9 +303,23 @@ def main():
     else:
         primary, shadow = scene.count_rays(width, height, spp, row_start, row_stride, my_rows)
     rays_rank = primary + shadow
+    e2e_steps = max(5, min(args.steps, 100))
+    e2e_rays_rank = rays_rank
+    if sweep:   # every orbit frame casts its own number of shadow rays: count each frame this rank renders
+        table = {}
+        for f in sorted({frame_of(i) for i in range(max(args.steps, e2e_steps))}):
+            table[f] = scene.count_rays(width, height, spp, camera=cams[f])
+        primary = sum(table[frame_of(i)][0] for i in range(args.steps)) / args.steps
+        shadow = sum(table[frame_of(i)][1] for i in range(args.steps)) / args.steps
+        rays_rank = primary + shadow                      # mean per timed step
+        e2e_rays_rank = sum(sum(table[frame_of(i)]) for i in range(e2e_steps)) / e2e_steps
     flush = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
-    def step():
+    def step(i=0):
+        if sweep:
+            rt.Renderer.render_rows(opts, scene, camera=cams[frame_of(i)], out_ptr=fb.data_ptr(),
+                                    stream=stream.cuda_stream)
+            return
         if peer:   # the traversal kernels' framebuffer stores ARE the gather (NVLink peer writes)
             rt.Renderer.render_row_blocks(opts, scene, row_start, row_stride, row_block, my_rows, frame_base,
                                           pitch=width * 4, absolute_rows=True, stream=stream.cuda_stream)
@@ -290,19 +338,19 @@ def main():
 
     sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else
                            os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]) if rank == 0 else None
-    for _ in range(args.warmup):
-        step()
+    for i in range(args.warmup):
+        step(i)
     barrier()
 
     # ---- value: K steps, device time from CUDA events on the launch stream --------------------
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_begin = time.time()
     w0 = time.perf_counter()
-    for a, b in ev:
+    for i, (a, b) in enumerate(ev):
         if flush is not None:
             flush.zero_()          # evict L2 (126 MB) between timed steps; outside the event pair
         a.record(stream)
-        step()
+        step(i)
         b.record(stream)
     barrier()
     wall_ms = (time.perf_counter() - w0) * 1e3
@@ -325,7 +373,6 @@ def main():
     # frames mode: rt_render_sweep (what `rtrace --frames` calls): the device-to-host copy of frame f
     # overlaps the render of frame f+1; the callback sees every frame in pinned host memory.
     # bands mode: rt_render_rows into a pinned host buffer, synchronously.
-    e2e_steps = max(5, min(args.steps, 100))
     seen = []
 
     def on_frame(f, arr):
@@ -340,7 +387,8 @@ def main():
                 rt.Renderer.render_rows(opts, scene, row_start=e_start, row_stride=e_stride, row_count=e_rows,
                                         out_ptr=pinned.ptr)
         else:
-            rt.Renderer.render_sweep(opts, scene, n, on_frame=on_frame, rgb=True)
+            rt.Renderer.render_sweep(opts, scene, n, on_frame=on_frame, rgb=True,
+                                     cameras=[cams[frame_of(i)] for i in range(n)] if sweep else None)
 
     e2e_run(3)
     barrier()
@@ -352,20 +400,20 @@ def main():
     clocks = sampler.stop(t_begin, t_end) if sampler else None
 
     # ---- max over ranks ------------------------------------------------------------------------
-    t = torch.tensor([dev_ms, e2e_ms, float(rays_rank)], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_ms, float(rays_rank), float(e2e_rays_rank)], dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        dev_ms, e2e_ms, rays_job = tmax[0].item(), tmax[1].item(), tsum[2].item()
+        dev_ms, e2e_ms, rays_job, e2e_rays_job = tmax[0].item(), tmax[1].item(), tsum[2].item(), tsum[3].item()
     else:
-        rays_job = float(rays_rank)
+        rays_job, e2e_rays_job = float(rays_rank), float(e2e_rays_rank)
 
     if rank == 0:
         ms_per_step = dev_ms / args.steps
         value = rays_job / (ms_per_step * 1e-3) / 1e6
-        e2e_value = rays_job / (e2e_ms / e2e_steps * 1e-3) / 1e6
+        e2e_value = e2e_rays_job / (e2e_ms / e2e_steps * 1e-3) / 1e6
         fpr, fpr_src = flop_per_ray(width, height, spp, level)
         try:
             peak_tf, eff_mhz = rt.measure_fp32_peak(local_rank)
@@ -395,8 +443,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong" if bands else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": "%s: pyramid level %d (%d spheres) at %dx%d, %d spp" % (
-                    args.workload, level, (4 ** level - 1) // 3, width, height, spp * spp),
+                "workload": workload_name(args.workload, level, width, height, spp),
                 "partition": (("interleaved row bands; kernels store into rank 0's frame through IPC peer memory (NVLink)"
                                " in blocks of 16 rows" if peer else "interleaved row bands + NCCL gather to rank 0") if bands else
                               "one whole frame per rank per step (frame-sharded sweep), no collective"),
