@@ -147,6 +147,15 @@ int rt_render_row_blocks(const rt_scene *s, const rt_camera *camera,
                          uint8_t *rgba_out, size_t pitch_bytes, int absolute_rows,
                          void *stream, rt_stats *stats);
 
+/* Undersampled preview of a frame (the reference README's "interactive rendering with undersampling",
+ * README.md:42-48; no counterpart in render.rs): the image is cut into step x step pixel blocks, the ONE
+ * ray of each block's first pixel (its top-left, 1 sample per pixel, exactly Renderer::render_region's value
+ * for that pixel at samples_per_pixel = 1) is traced and its colour fills the block.  step = 1 is the
+ * plain 1-spp frame; the cost falls with step^2.  rgba_out: host or device buffer of width*height*4 bytes;
+ * `stream` as in rt_render_rows (a device output is not synchronised). */
+int rt_render_preview(const rt_scene *s, const rt_camera *camera, uint32_t width, uint32_t height, uint32_t step,
+                      uint8_t *rgba_out, size_t rgba_len, void *stream);
+
 /* Whole frame to a host or device buffer of width*height*4 bytes on the scene's GPU. */
 int rt_render_frame(const rt_scene *s, const rt_camera *camera,
                     uint32_t width, uint32_t height, uint32_t spp,
@@ -155,7 +164,9 @@ int rt_render_frame(const rt_scene *s, const rt_camera *camera,
 /* A sweep of n_frames frames (cameras[f], or the reference camera when cameras is
  * NULL) with the device-to-host copy of frame f overlapping the render of frame
  * f+1.  `cb` is called on the calling thread, in frame order, with a pinned host
- * buffer that stays valid until the callback returns.  This is the end-to-end
+ * buffer that stays valid until the callback returns.  The scene's scratch is
+ * locked for the whole sweep: the callback must not render with the same scene
+ * (other scenes and other threads' calls on this scene simply wait).  This is the end-to-end
  * path of the orbit sweep (BASELINE C5) and what `rtrace --frames` uses. */
 typedef void (*rt_frame_callback)(void *user, uint32_t frame, const uint8_t *rgba, size_t len);
 int rt_render_sweep(const rt_scene *s, const rt_camera *cameras, uint32_t n_frames,
@@ -170,9 +181,10 @@ int rt_render_sweep_rgb(const rt_scene *s, const rt_camera *cameras, uint32_t n_
                         rt_frame_callback cb, void *user, rt_stats *stats);
 
 /* Whole frame on ngpu GPUs of this process (devices 0..ngpu-1): the scene is
- * replicated, rows are interleaved (GPU g renders rows g, g+ngpu, ...) and every
- * GPU's kernel stores its pixels directly into GPU 0's frame through peer memory
- * (NVLink); without peer access the bands are gathered by strided copies.  The
+ * replicated, GPU g renders blocks of 16 consecutive rows ngpu blocks apart
+ * (whole cull tiles stay together) and its kernels store the pixels directly into
+ * GPU 0's frame through peer memory (NVLink); without peer access GPU g renders
+ * rows g, g+ngpu, ... and the bands are gathered by strided copies.  The
  * frame is then copied to rgba_out (host).  scenes[g] must live on device g.  Replaces the
  * thread pool + sync_channel of Renderer::render (render.rs:271-307). */
 int rt_render_frame_multi(rt_scene *const *scenes, int ngpu, const rt_camera *camera,

@@ -233,6 +233,7 @@ bool eye_outside_root_bound(const rt::RenderParams &p) {
 }
 
 int kernel_variant(const rt::RenderParams &p) {
+    if (p.col_count) return g_variant == RT_VARIANT_WARP ? RT_KERNEL_WARP : RT_KERNEL_LANE;  // bucket-sized window
     const bool tile_ok = rt_tile_supported(p) && (!p.has_basis || orthonormal(p.basis)) && eye_outside_root_bound(p);
     switch (g_variant) {
         case RT_VARIANT_LANE:
@@ -280,14 +281,14 @@ int prepare_phased(rt_scene *s, rt::RenderParams &p, cudaStream_t stream) {
     size_t wb = 0, hb = 0;
     uint32_t units = 0;
     rt_phased_scratch(p.width, p.row_count, p.spp, tile_shape(), &wb, &hb, &units);
-    if (const char *cap = getenv("RTRACE_POOL_UNITS")) {  // tests: a tiny pool exercises the overflow fallback
-        if (*cap) units = (uint32_t)strtoul(cap, nullptr, 10);
-    }
+    const char *cap = getenv("RTRACE_POOL_UNITS");  // tests: a tiny pool exercises the overflow fallback
+    const bool forced_pool = cap && *cap;
+    if (forced_pool) units = (uint32_t)strtoul(cap, nullptr, 10);
     std::lock_guard<std::mutex> lock(s->mu_phased);
     rt_scene::Phased &ph = s->phased[stream];
     int rc = ensure_typed(&ph.winner, &ph.winner_cap, wb);
     if (rc == RT_OK) rc = ensure_typed(&ph.hdr, &ph.hdr_cap, hb);
-    if (rc == RT_OK && ph.pool_units != units && (ph.pool_units < units || getenv("RTRACE_POOL_UNITS"))) {
+    if (rc == RT_OK && ph.pool_units != units && (ph.pool_units < units || forced_pool)) {
         size_t cap = (size_t)ph.pool_units * sizeof(uint4);
         rc = ensure_typed(&ph.pool, &cap, (size_t)units * sizeof(uint4));
         if (rc == RT_OK) ph.pool_units = units;
@@ -489,12 +490,16 @@ int rt_scene_device(const rt_scene *s) { return s ? s->device : fail(RT_ERR_INVA
 static int render_rows_impl(rt_scene *s, const rt_camera *camera, uint32_t width, uint32_t height, uint32_t spp,
                             uint32_t row_start, uint32_t row_stride, uint32_t row_count, uint8_t *rgba_out,
                             size_t pitch_bytes, uint8_t *kinds_out, cudaStream_t stream, rt_stats *stats,
-                            uint64_t *count_hits, uint64_t *count_shadow) {
+                            uint64_t *count_hits, uint64_t *count_shadow, uint32_t col_start = 0,
+                            uint32_t col_count = 0) {
     int rc = check_frame_args(s, width, height, spp, row_start, row_stride, row_count);
     if (rc != RT_OK) return rc;
     const bool counting = count_shadow != nullptr;
     if (!rgba_out && !counting) return fail(RT_ERR_INVALID, "rgba_out is NULL");
-    const size_t row_bytes = (size_t)width * 4;
+    // col_count > 0: only columns col_start .. col_start + col_count - 1, packed from byte 0 of each output row
+    if ((uint64_t)col_start + col_count > width) return fail(RT_ERR_INVALID, "columns %u..%u leave the %u-pixel row", col_start, col_start + col_count, width);
+    const uint32_t cols = col_count ? col_count : width;
+    const size_t row_bytes = (size_t)cols * 4;
     if (pitch_bytes == 0) pitch_bytes = row_bytes;
     if (pitch_bytes < row_bytes || (pitch_bytes & 3)) return fail(RT_ERR_INVALID, "pitch %zu too small or not a multiple of 4", pitch_bytes);
     if (stats) memset(stats, 0, sizeof(*stats));
@@ -518,7 +523,7 @@ static int render_rows_impl(rt_scene *s, const rt_camera *camera, uint32_t width
     if (out_on_device && (((uintptr_t)rgba_out) & 3)) return fail(RT_ERR_INVALID, "device rgba_out must be 4-byte aligned");
     int kinds_dev = -1;
     const bool kinds_on_device = kinds_out && is_device_ptr(kinds_out, &kinds_dev);
-    const size_t kinds_bytes = (size_t)width * row_count * spp * spp;
+    const size_t kinds_bytes = (size_t)cols * row_count * spp * spp;
 
     if (g_out_abs && !out_on_device) return fail(RT_ERR_INVALID, "absolute row addressing needs a device (or peer) frame buffer");
     const bool need_lock = !out_on_device || (kinds_out && !kinds_on_device) || counting || stats;
@@ -527,6 +532,8 @@ static int render_rows_impl(rt_scene *s, const rt_camera *camera, uint32_t width
 
     rt::RenderParams p;
     fill_params(s, camera, width, height, spp, row_start, row_stride, row_count, p);
+    p.col_start = col_count ? col_start : 0;
+    p.col_count = col_count;
     if (out_on_device) {
         p.out = rgba_out;
         p.pitch = pitch_bytes;
@@ -587,7 +594,7 @@ static int render_rows_impl(rt_scene *s, const rt_camera *camera, uint32_t width
         CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
         stats->kernel_ms = ms;
         stats->total_ms = now_ms() - t0;
-        stats->primary_rays = (uint64_t)width * row_count * spp * spp;
+        stats->primary_rays = (uint64_t)cols * row_count * spp * spp;
         stats->shadow_rays = counting ? ctr[1] : 0;
         stats->kernel_launches = (uint32_t)launches_per_frame(p);
         stats->gpus = 1;
@@ -629,18 +636,10 @@ int rt_render_region(const rt_scene *s, uint16_t width, uint16_t height, uint16_
     if (l == 0 && r == width)
         return render_rows_impl(const_cast<rt_scene *>(s), nullptr, width, height, spp, b, 1, rh, rgba_out, 0, nullptr,
                                 nullptr, nullptr, nullptr, nullptr);
-    // A column sub-range: render the full rows on the device and copy out the window.
-    rt_scene *ms = const_cast<rt_scene *>(s);
-    DeviceGuard guard(ms->device);
-    uint8_t *rows = nullptr;
-    CUDA_TRY(cudaMalloc(&rows, (size_t)width * rh * 4));
-    int rc = render_rows_impl(ms, nullptr, width, height, spp, b, 1, rh, rows, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
-    if (rc == RT_OK) {
-        cudaError_t e = cudaMemcpy2D(rgba_out, (size_t)rw * 4, rows + (size_t)l * 4, (size_t)width * 4, (size_t)rw * 4, rh, cudaMemcpyDefault);
-        if (e != cudaSuccess) rc = fail(RT_ERR_CUDA, "cudaMemcpy2D: %s", cudaGetErrorString(e));
-    }
-    cudaFree(rows);
-    return rc;
+    // A bucket (render.rs:273-298 cuts the frame into 64x64 of them): the per-lane kernel renders just the
+    // window, so the cost of a region is proportional to its area.
+    return render_rows_impl(const_cast<rt_scene *>(s), nullptr, width, height, spp, b, 1, rh, rgba_out, 0, nullptr,
+                            nullptr, nullptr, nullptr, nullptr, l, rw);
 }
 
 int rt_render_frame(const rt_scene *s, const rt_camera *camera, uint32_t width, uint32_t height, uint32_t spp,
@@ -649,6 +648,49 @@ int rt_render_frame(const rt_scene *s, const rt_camera *camera, uint32_t width, 
     return render_rows_impl(const_cast<rt_scene *>(s), camera, width, height, spp, 0, 1, height, rgba_out, 0, nullptr,
                             nullptr, stats, nullptr, nullptr);
 }
+
+int rt_render_preview(const rt_scene *cs, const rt_camera *camera, uint32_t width, uint32_t height, uint32_t step,
+                      uint8_t *rgba_out, size_t rgba_len, void *stream_) {
+    rt_scene *s = const_cast<rt_scene *>(cs);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (step == 0 || step > 1024u) return fail(RT_ERR_INVALID, "step must be in 1..1024 (got %u)", step);
+    int rc = check_frame_args(s, width, height, 1, 0, 1, height);
+    if (rc != RT_OK) return rc;
+    if (!rgba_out) return fail(RT_ERR_INVALID, "rgba_out is NULL");
+    const size_t row_bytes = (size_t)width * 4, frame_bytes = row_bytes * height;
+    if (rgba_len < frame_bytes) return fail(RT_ERR_BUFFER, "rgba_out holds %zu bytes, frame needs %zu", rgba_len, frame_bytes);
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(RT_ERR_CUDA, "cannot select device %d", s->device);
+    int out_dev = -1;
+    const bool out_on_device = is_device_ptr(rgba_out, &out_dev);
+    if (out_on_device && out_dev != s->device) return fail(RT_ERR_INVALID, "rgba_out lives on device %d, the scene on device %d", out_dev, s->device);
+    if (out_on_device && (((uintptr_t)rgba_out) & 3)) return fail(RT_ERR_INVALID, "device rgba_out must be 4-byte aligned");
+    std::unique_lock<std::mutex> lock(s->mu, std::defer_lock);
+    if (!out_on_device) lock.lock();  // the staging frame is per scene
+    rt::RenderParams p;
+    const uint32_t bx = (width + step - 1) / step, by = (height + step - 1) / step;  // blocks = traced pixels
+    fill_params(s, camera, width, height, 1, 0, 1, by, p);
+    p.col_count = bx;
+    p.px_step = step;
+    p.pitch = row_bytes;
+    if (out_on_device) {
+        p.out = rgba_out;
+    } else {
+        rc = ensure(&s->d_fb, &s->d_fb_cap, frame_bytes);
+        if (rc != RT_OK) return rc;
+        p.out = s->d_fb;
+    }
+    cudaError_t e = rt_launch_render_preview(p, stream);
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
+    if (!out_on_device) {
+        CUDA_TRY(cudaMemcpyAsync(rgba_out, s->d_fb, frame_bytes, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    return RT_OK;
+}
+
+static int sweep_locked(rt_scene *s, const rt_camera *cameras, uint32_t n_frames, uint32_t width, uint32_t height,
+                        uint32_t spp, rt_frame_callback cb, void *user, rt_stats *stats, bool rgb);
 
 static int sweep_impl(const rt_scene *cs, const rt_camera *cameras, uint32_t n_frames, uint32_t width, uint32_t height,
                       uint32_t spp, rt_frame_callback cb, void *user, rt_stats *stats, bool rgb) {
@@ -660,6 +702,18 @@ static int sweep_impl(const rt_scene *cs, const rt_camera *cameras, uint32_t n_f
     DeviceGuard guard(s->device);
     if (!guard.ok) return fail(RT_ERR_CUDA, "cannot select device %d", s->device);
     std::lock_guard<std::mutex> lock(s->mu);
+    rc = sweep_locked(s, cameras, n_frames, width, height, spp, cb, user, stats, rgb);
+    if (rc != RT_OK) {  // leave no render or copy in flight on the double buffers (keeps the first error text)
+        if (s->own_stream) cudaStreamSynchronize(s->own_stream);
+        if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
+        cudaGetLastError();
+    }
+    return rc;
+}
+
+static int sweep_locked(rt_scene *s, const rt_camera *cameras, uint32_t n_frames, uint32_t width, uint32_t height,
+                        uint32_t spp, rt_frame_callback cb, void *user, rt_stats *stats, bool rgb) {
+    int rc = RT_OK;
     const double t0 = now_ms();
     const size_t row_bytes = (size_t)width * 4, frame_bytes = row_bytes * height;
     const size_t out_bytes = rgb ? (size_t)width * height * 3 : frame_bytes;
@@ -758,6 +812,8 @@ int rt_render_frame_multi(rt_scene *const *scenes, int ngpu, const rt_camera *ca
         if (rc != RT_OK) return rc;
     }
     uint8_t *frame = root->d_frame;
+    std::vector<char> launched((size_t)ngpu, 0);  // GPUs whose share of the rows is not empty
+    uint32_t launches = 0;
     for (int g = 0; g < ngpu; g++) {
         rt_scene *s = scenes[g];
         DeviceGuard guard(s->device);
@@ -803,17 +859,18 @@ int rt_render_frame_multi(rt_scene *const *scenes, int ngpu, const rt_camera *ca
             int rc = launch(s, p, false, s->own_stream);
             if (rc != RT_OK) return rc;
         }
+        launched[(size_t)g] = 1;
+        launches += (uint32_t)launches_per_frame(p);
         if (stats) CUDA_TRY(cudaEventRecord(s->ev1, s->own_stream));
         if (!peer)  // no peer access: strided copy, the pitch de-interleaves the band into the frame
             CUDA_TRY(cudaMemcpy2DAsync(frame + row_bytes * g, row_bytes * ngpu, s->d_fb, row_bytes, row_bytes, rows, cudaMemcpyDefault, s->own_stream));
-        (void)rows;
     }
     double kmax = 0.0;
     for (int g = ngpu - 1; g >= 0; g--) {
         rt_scene *s = scenes[g];
         DeviceGuard guard(s->device);
         CUDA_TRY(cudaStreamSynchronize(s->own_stream));
-        if (stats && height > (uint32_t)g) {
+        if (stats && launched[(size_t)g]) {
             float ms = 0.0f;
             CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
             if (ms > kmax) kmax = ms;
@@ -827,7 +884,7 @@ int rt_render_frame_multi(rt_scene *const *scenes, int ngpu, const rt_camera *ca
         stats->kernel_ms = kmax;
         stats->total_ms = now_ms() - t0;
         stats->primary_rays = (uint64_t)width * height * spp * spp;
-        stats->kernel_launches = (uint32_t)ngpu;
+        stats->kernel_launches = launches;
         stats->gpus = (uint32_t)ngpu;
     }
     return RT_OK;

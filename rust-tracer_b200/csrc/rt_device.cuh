@@ -104,6 +104,13 @@ struct RenderParams {
     uint32_t *winner;       // per sample: index of the closest leaf
     uint8_t *kinds;                    // optional per-sample classification
     unsigned long long *ray_counters;  // optional {primary_hits, shadow_rays}
+    // Column window of Renderer::render_region (render.rs:218-255, a bucket): pixels col_start ..
+    // col_start + col_count - 1 of each row, stored from byte 0 of the output row.  col_count 0 = the
+    // whole width.  Only the per-lane kernels (LANE / WARP) take a window; the API routes it there.
+    uint32_t col_start, col_count;
+    // Undersampled preview (rt_render_preview): lane (lx, j) traces the one ray of pixel (lx*px_step, j*px_step)
+    // and stores its colour into the whole px_step x px_step block.  Read by the PREVIEW instantiation only.
+    uint32_t px_step;
 };
 
 // Local row j of this launch -> image row: blocks of 2^shift consecutive rows, row_stride apart

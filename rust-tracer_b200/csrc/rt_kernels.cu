@@ -73,15 +73,18 @@ RT_DEV void warp_traverse(const float4 *__restrict__ sph, const uint32_t *__rest
 // ---------------------------------------------------------------------------
 // The fused pixel kernel.
 // ---------------------------------------------------------------------------
-template <int VARIANT, bool DIAG>
+template <int VARIANT, bool DIAG, bool PREVIEW = false>
 __global__ void __launch_bounds__(BLOCK_THREADS) render_kernel(const RenderParams p) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const uint32_t x = blockIdx.x * (TILE_W * WARPS_X) + (warp % WARPS_X) * TILE_W + (lane % TILE_W);
+    const uint32_t lx = blockIdx.x * (TILE_W * WARPS_X) + (warp % WARPS_X) * TILE_W + (lane % TILE_W);
     const uint32_t j = blockIdx.y * (TILE_H * WARPS_Y) + (warp / WARPS_X) * TILE_H + (lane / TILE_W);
-    const bool inside = x < p.width && j < p.row_count;
+    const uint32_t cols = p.col_count ? p.col_count : p.width;  // column window (render_region buckets)
+    const uint32_t step = PREVIEW ? p.px_step : 1u;             // preview: one traced pixel per step x step block
+    const uint32_t x = (p.col_start + lx) * step;               // image column: what the ray is generated from
+    const bool inside = lx < cols && j < p.row_count;
     if (VARIANT == RT_KERNEL_LANE && !inside) return;
-    const uint32_t y = image_row(p, j);
+    const uint32_t y = image_row(p, j) * step;
 
     const ShadeConsts K = shade_consts();
     const V3 eye = v3(p.eye[0], p.eye[1], p.eye[2]);
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) render_kernel(const RenderParam
                 }
             }
             if (DIAG && p.kinds && inside)
-                p.kinds[((size_t)j * p.width + x) * (p.spp * p.spp) + ssx * p.spp + ssy] = kind;
+                p.kinds[((size_t)j * cols + lx) * (p.spp * p.spp) + ssx * p.spp + ssy] = kind;
         }
     }
 
@@ -152,7 +155,15 @@ __global__ void __launch_bounds__(BLOCK_THREADS) render_kernel(const RenderParam
         c = vmulf(c, recip);
         alpha = fmul(alpha, recip);
         uint32_t px = scale_u8(c.x) | (scale_u8(c.y) << 8) | (scale_u8(c.z) << 16) | (scale_u8(alpha) << 24);
-        *reinterpret_cast<uint32_t *>(p.out + (size_t)out_row(p, j) * p.pitch + (size_t)x * 4) = px;
+        if (PREVIEW) {  // the block's pixels that lie inside the image, each row of the block contiguous
+            const uint32_t x1 = min(x + step, p.width), y1 = min(y + step, p.height);
+            for (uint32_t yy = y; yy < y1; yy++) {
+                uint32_t *row = reinterpret_cast<uint32_t *>(p.out + (size_t)yy * p.pitch);
+                for (uint32_t xx = x; xx < x1; xx++) row[xx] = px;
+            }
+        } else {
+            *reinterpret_cast<uint32_t *>(p.out + (size_t)out_row(p, j) * p.pitch + (size_t)lx * 4) = px;
+        }
     }
     if (DIAG && p.ray_counters) {
         if (!inside) {
@@ -264,7 +275,8 @@ using namespace rt;
 
 cudaError_t rt_launch_render(int variant, bool diag, const RenderParams &p, cudaStream_t stream) {
     dim3 block(BLOCK_THREADS);
-    dim3 grid((p.width + TILE_W * WARPS_X - 1) / (TILE_W * WARPS_X),
+    const uint32_t cols = p.col_count ? p.col_count : p.width;
+    dim3 grid((cols + TILE_W * WARPS_X - 1) / (TILE_W * WARPS_X),
               (p.row_count + TILE_H * WARPS_Y - 1) / (TILE_H * WARPS_Y));
     if (grid.x == 0 || grid.y == 0) return cudaSuccess;
     if (variant == RT_KERNEL_LANE) {
@@ -278,6 +290,16 @@ cudaError_t rt_launch_render(int variant, bool diag, const RenderParams &p, cuda
         else
             render_kernel<RT_KERNEL_WARP, false><<<grid, block, 0, stream>>>(p);
     }
+    return cudaGetLastError();
+}
+
+// One ray per px_step x px_step block (p.col_count x p.row_count blocks), colour replicated over the block.
+cudaError_t rt_launch_render_preview(const RenderParams &p, cudaStream_t stream) {
+    dim3 block(BLOCK_THREADS);
+    dim3 grid((p.col_count + TILE_W * WARPS_X - 1) / (TILE_W * WARPS_X),
+              (p.row_count + TILE_H * WARPS_Y - 1) / (TILE_H * WARPS_Y));
+    if (grid.x == 0 || grid.y == 0 || p.px_step == 0) return cudaSuccess;
+    render_kernel<RT_KERNEL_LANE, false, true><<<grid, block, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -11,6 +11,7 @@ struct RenderParams;
 }
 
 cudaError_t rt_launch_render(int variant, bool diag, const rt::RenderParams &p, cudaStream_t stream);
+cudaError_t rt_launch_render_preview(const rt::RenderParams &p, cudaStream_t stream);
 cudaError_t rt_launch_trace_rays(const float4 *sph, const uint32_t *skip, uint32_t n, size_t n_rays,
                                  const float *rays, float *hits, cudaStream_t stream);
 cudaError_t rt_launch_pack_rgb(const uint8_t *rgba, uint8_t *rgb, size_t n_px, cudaStream_t stream);

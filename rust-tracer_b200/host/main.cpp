@@ -11,7 +11,8 @@
 // longer exists -- the GPU path ignores them.
 // Additive flags: --level=L (scene depth, default 8 as at render.rs:147),
 // --gpus=N / RTRACE_GPUS (default 1), --frames=K (orbit sweep; frame f goes to
-// <stem>.f.tga, frame 0 is the reference camera), --stats (summary on stderr).
+// <stem>.f.tga, frame 0 is the reference camera), --stats (summary on stderr), --buckets (the reference's 64x64 bucket
+// schedule through Renderer::render_region instead of one launch per frame).
 #include <cerrno>
 #include <chrono>
 #include <cmath>
@@ -52,7 +53,10 @@ const char *USAGE =
     "        --gpus <N>                         GPUs to render on; rows are interleaved [default: 1 or RTRACE_GPUS]\n"
     "        --frames <K>                       Render a K-frame orbit of the camera [default: 1]\n"
     "        --format <ppm|tga>                 File contents: the reference's binary PPM, or a real TGA [default: ppm]\n"
+    "        --preview <N>                      Undersampled preview: trace one pixel per NxN block (1 sample) [default: off]\n"
     "        --stats                            Print a timing summary to stderr\n"
+    "        --buckets                          Render 64x64 buckets one by one in the reference's order (sizes must\n"
+    "                                           be multiples of 64, as in the reference); default is whole frames\n"
     "\n"
     "ARGS:\n"
     "    <output>    Either a file with .tga extension, or - to write file to stdout\n";
@@ -89,8 +93,8 @@ unsigned long long parse_or_panic(const std::string &s, unsigned long long max, 
 }
 
 struct Args {
-    std::string width, height, ssp, numcores, output, level, gpus, frames, format;
-    bool has_output = false, stats = false;
+    std::string width, height, ssp, numcores, output, level, gpus, frames, format, preview;
+    bool has_output = false, stats = false, buckets = false;
 };
 
 Args parse_args(int argc, char **argv) {
@@ -101,7 +105,8 @@ Args parse_args(int argc, char **argv) {
     };
     const Opt opts[] = {{"--width", &Args::width},   {"--height", &Args::height}, {"--samples-per-pixel", &Args::ssp},
                         {"--num-cores", &Args::numcores}, {"--level", &Args::level},   {"--gpus", &Args::gpus},
-                        {"--frames", &Args::frames}, {"--format", &Args::format}};
+                        {"--frames", &Args::frames}, {"--format", &Args::format},
+                        {"--preview", &Args::preview}};
     bool only_positional = false;
     for (int i = 1; i < argc; i++) {
         std::string arg = argv[i];
@@ -119,6 +124,10 @@ Args parse_args(int argc, char **argv) {
         }
         if (!only_positional && arg == "--stats") {
             a.stats = true;
+            continue;
+        }
+        if (!only_positional && arg == "--buckets") {
+            a.buckets = true;
             continue;
         }
         if (!only_positional && arg.size() > 2 && arg[0] == '-' && arg[1] == '-') {
@@ -230,6 +239,7 @@ int main(int argc, char **argv) {
     if (!args.format.empty() && args.format != "ppm" && args.format != "tga")
         usage_error("'" + args.format + "' isn't a valid value for '--format <ppm|tga>'");
     const bool real_tga = args.format == "tga";
+    const unsigned preview = args.preview.empty() ? 0u : (unsigned)parse_or_panic(args.preview, 1024, "preview");
     if (options.width == 0 || options.height == 0) {
         fprintf(stderr, "thread 'main' panicked at 'width and height must be at least 1'\n");
         return 101;
@@ -253,7 +263,7 @@ int main(int argc, char **argv) {
             if (!fp) throw Panic(std::string("called `Result::unwrap()` on an `Err` value: ") + strerror(errno));
             return FileOrAnyWriter::file_writer(fp);
         };
-        if (frames > 1 && gpus == 1) {
+        if (frames > 1 && gpus == 1 && !preview && !args.buckets) {
             // orbit sweep on one GPU: copy-out of frame f overlaps the render of frame f+1
             std::vector<rt_camera> cams;
             for (unsigned f = 0; f < frames; f++) cams.push_back(orbit_camera(f, frames));
@@ -284,7 +294,9 @@ int main(int argc, char **argv) {
                     else sink.reset(new PPMStdoutRGBABufferWriter(true, &output));
                     RGBABufferWriter &writer = *sink;
                     auto r0 = clk::now();
-                    Renderer::render(options, scene, writer, frames > 1 ? &cam : nullptr, &st);
+                    if (preview) Renderer::render_preview(options, scene, writer, preview, frames > 1 ? &cam : nullptr);
+                    else if (args.buckets) Renderer::render_buckets(options, scene, writer);  // the reference's 64x64 schedule
+                    else Renderer::render(options, scene, writer, frames > 1 ? &cam : nullptr, &st);
                     render_ms += std::chrono::duration<double, std::milli>(clk::now() - r0).count();
                     kernel_ms += st.kernel_ms;
                 }  // final write on drop (render.rs:331-335)

@@ -280,6 +280,48 @@ struct Renderer {
         writer.write_rgba_buffer(frame);
     }
 
+    // render.rs:218-255: the pixels of `buf.region()` (a bucket, or any window of the frame), row-major from
+    // row b, on the scene's first GPU.  Same seam as the reference's, for callers that schedule regions
+    // themselves (region-of-interest rendering, README "season 2").
+    static void render_region(const RenderOptions &o, const Scene &scene, RGBABuffer &buf) {
+        const ImageRegion &r = buf.region();
+        rt_check(rt_render_region(scene.replicas()[0], o.width, o.height, o.samples_per_pixel, r.l, r.b, r.r, r.t,
+                                  buf.data(), buf.len()),
+                 "Renderer::render_region");
+    }
+
+    // Undersampled preview (README.md:42-48 "interactive rendering with undersampling"; extension): one traced
+    // pixel per step x step block, handed to the writer as one full-size buffer.
+    static void render_preview(const RenderOptions &o, const Scene &scene, RGBABufferWriter &writer, uint32_t step,
+                               const rt_camera *camera = nullptr) {
+        writer.begin(o.width, o.height);
+        ImageRegion full;
+        full.l = 0, full.r = o.width, full.b = 0, full.t = o.height;
+        RGBABuffer frame(full);
+        rt_check(rt_render_preview(scene.replicas()[0], camera, o.width, o.height, step, frame.data(), frame.len(), nullptr),
+                 "Renderer::render_preview");
+        writer.write_rgba_buffer(frame);
+    }
+
+    // The reference's own schedule (render.rs:265-309): the frame cut into 64x64 buckets, row-major y then x,
+    // each rendered by render_region and handed to the writer as it completes.  Kept for conformance of the
+    // writer seam (buckets "might be anywhere", render.rs:25-27) and selected by `rtrace --buckets`; render()
+    // above is the fast path.  Like the reference it insists on multiples of 64.
+    static void render_buckets(const RenderOptions &o, const Scene &scene, RGBABufferWriter &writer) {
+        const uint16_t bucket = 64;
+        if (o.width % bucket != 0) throw Panic("assertion failed: o.width % BUCKET_SIZE == 0");
+        if (o.height % bucket != 0) throw Panic("assertion failed: o.height % BUCKET_SIZE == 0");
+        writer.begin(o.width, o.height);
+        for (uint32_t y = 0; y < o.height; y += bucket)
+            for (uint32_t x = 0; x < o.width; x += bucket) {
+                ImageRegion r;
+                r.l = (uint16_t)x, r.r = (uint16_t)(x + bucket), r.b = (uint16_t)y, r.t = (uint16_t)(y + bucket);
+                RGBABuffer buf(r);
+                render_region(o, scene, buf);
+                writer.write_rgba_buffer(buf);
+            }
+    }
+
     // A sweep of frames on one GPU (extension): the device-to-host copy of frame f overlaps the
     // render of frame f+1 (rt_render_sweep).  `sink(f, bytes, len)` is called once per frame, in order;
     // with rgb = true the frames arrive as RGB8 (the body of the P6 file, alpha already dropped).

@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "rt_last_error", "rt_version", "rt_device_count", "rt_set_device", "rt_set_variant",
     "rt_scene_create", "rt_scene_create_default", "rt_scene_create_from_nodes", "rt_scene_destroy",
     "rt_scene_counts", "rt_scene_export_nodes", "rt_flatten_pyramid_host", "rt_scene_light", "rt_scene_eye",
-    "rt_scene_device", "rt_render_region", "rt_render_rows", "rt_render_row_blocks", "rt_render_frame", "rt_render_sweep", "rt_render_sweep_rgb",
+    "rt_scene_device", "rt_render_region", "rt_render_preview", "rt_render_rows", "rt_render_row_blocks", "rt_render_frame", "rt_render_sweep", "rt_render_sweep_rgb",
     "rt_render_frame_multi",
     "rt_count_rays", "rt_trace_rays", "rt_measure_fp32_peak", "rt_microbench_fp32", "rt_selftest_math", "rt_debug_phased_tiles", "rt_host_alloc", "rt_host_free", "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_memcpy",
 ]
@@ -80,6 +80,7 @@ def lib():
     L.rt_render_row_blocks.argtypes = [vp, C.POINTER(Camera), u32, u32, u32, u32, u32, u32, u32, u8p, C.c_size_t,
                                        C.c_int, vp, C.POINTER(Stats)]
     L.rt_render_frame.argtypes = [vp, C.POINTER(Camera), u32, u32, u32, u8p, C.c_size_t, C.POINTER(Stats)]
+    L.rt_render_preview.argtypes = [vp, C.POINTER(Camera), u32, u32, u32, u8p, C.c_size_t, vp]
     L.rt_render_sweep.argtypes = [vp, C.POINTER(Camera), u32, u32, u32, u32, FRAME_CALLBACK, vp, C.POINTER(Stats)]
     L.rt_render_sweep_rgb.argtypes = L.rt_render_sweep.argtypes
     L.rt_render_frame_multi.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(Camera), u32, u32, u32, u8p, C.c_size_t,
@@ -312,6 +313,18 @@ class Renderer:
         _check(lib().rt_render_frame(scene.handle, C.byref(camera) if camera is not None else None, w, h, spp,
                                      out_ptr, w * h * 4, C.byref(st) if st is not None else None))
         return (out, st) if want_stats else out
+
+    @staticmethod
+    def render_preview(options, scene, step, camera=None, out_ptr=None, stream=None):
+        """Undersampled preview (rt_render_preview): one traced pixel per step x step block, 1 sample per pixel."""
+        w, h = options.width, options.height
+        out = None
+        if out_ptr is None:
+            out = np.empty((h, w, 4), np.uint8)
+            out_ptr = out.ctypes.data
+        _check(lib().rt_render_preview(scene.handle, C.byref(camera) if camera is not None else None, w, h, step,
+                                       out_ptr, w * h * 4, stream))
+        return out
 
     @staticmethod
     def render_sweep(options, scene, n_frames, cameras=None, on_frame=None, rgb=False):

@@ -107,6 +107,35 @@ def test_sizes_the_reference_rejects_and_extensions(rtrace, tmp_path):
     assert frames[0] == one.stdout and frames[1] != frames[0]
 
 
+@pytest.mark.gpu
+def test_bucket_schedule_writes_the_same_file(rtrace, tmp_path):
+    """--buckets: the reference's own schedule (render.rs:265-309), 64x64 buckets through render_region and
+    the writer seam one by one; the file equals the whole-frame path's, and sizes that are not multiples of
+    64 panic as in the reference (render.rs:265-266)."""
+    a = run(rtrace, "--width=256", "--height=192", "--samples-per-pixel=2", "-")
+    b = run(rtrace, "--width=256", "--height=192", "--samples-per-pixel=2", "--buckets", "b.tga", cwd=str(tmp_path))
+    assert a.returncode == 0 and b.returncode == 0, b.stderr
+    assert (tmp_path / "b.tga").read_bytes() == a.stdout
+    r = run(rtrace, "--width=100", "--height=64", "--buckets", "c.tga", cwd=str(tmp_path))
+    assert r.returncode == 101 and b"BUCKET_SIZE" in r.stderr
+
+
+@pytest.mark.gpu
+def test_preview_flag(rtrace, tmp_path):
+    """--preview N (README.md:42-48, extension): blocks of NxN pixels share the colour of their first pixel."""
+    w, h, n = 96, 64, 8
+    full = run(rtrace, "--width=%d" % w, "--height=%d" % h, "-")
+    prev = run(rtrace, "--width=%d" % w, "--height=%d" % h, "--preview=%d" % n, "-")
+    assert full.returncode == 0 and prev.returncode == 0, prev.stderr
+    hdr = len(b"P6\n96 64\n255\n")
+    f, p = full.stdout[hdr:], prev.stdout[hdr:]
+    assert len(p) == w * h * 3
+    for y in range(h):
+        for x in range(w):
+            a = ((y // n * n) * w + (x // n * n)) * 3
+            assert p[(y * w + x) * 3:(y * w + x) * 3 + 3] == f[a:a + 3]
+
+
 def test_format_flag_is_validated(rtrace, tmp_path):
     assert run(rtrace, "--format=bmp", "o.tga", cwd=str(tmp_path)).returncode == 1
 

@@ -94,6 +94,31 @@ def test_render_region_semantics(rt, oracle, gpu_scene8, oracle_scene8):
     assert e.value.code == rt.RT_ERR_INVALID
 
 
+def test_buckets_tile_the_frame(rt, oracle_scene8, gpu_scene8):
+    """The reference's schedule (render.rs:273-298): 64x64 buckets, each a render_region call, reassemble
+    the `make image`-shaped frame; a bucket's cost is its own area (the per-lane kernel takes the window)."""
+    w, h, spp = 256, 192, 4
+    o = rt.RenderOptions(w, h, spp)
+    full, _ = oracle_scene8.render(w, h, spp)
+    got = np.zeros_like(full)
+    for y in range(0, h, 64):
+        for x in range(0, w, 64):
+            got[y:y + 64, x:x + 64] = rt.Renderer.render_region(o, gpu_scene8, x, y, x + 64, y + 64)
+    assert_same(got, full, "64x64 buckets")
+
+
+@pytest.mark.parametrize("w,h,step", [(97, 61, 1), (97, 61, 4), (200, 150, 7), (64, 64, 64), (50, 40, 100)])
+def test_undersampled_preview(rt, oracle_scene8, gpu_scene8, w, h, step):
+    """rt_render_preview: every step x step block carries the reference's 1-spp value of its first pixel."""
+    full, _ = oracle_scene8.render(w, h, 1)
+    ys, xs = (np.arange(h) // step) * step, (np.arange(w) // step) * step
+    got = rt.Renderer.render_preview(rt.RenderOptions(w, h, 1), gpu_scene8, step)
+    assert_same(got, full[ys][:, xs], "preview step %d" % step)
+    with pytest.raises(rt.RtError) as e:
+        rt.Renderer.render_preview(rt.RenderOptions(w, h, 1), gpu_scene8, 0)
+    assert e.value.code == rt.RT_ERR_INVALID
+
+
 def test_interleaved_rows_and_pitch(rt, oracle_scene8, gpu_scene8):
     """The multi-GPU partition: rows g, g+G, ... rendered independently reassemble the frame."""
     w, h, spp, G = 120, 67, 2, 4
