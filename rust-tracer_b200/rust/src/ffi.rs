@@ -37,6 +37,8 @@ extern "C" {
     pub fn rt_scene_counts(s: *const RtScene, groups: *mut u64, items: *mut u64) -> c_int;
     pub fn rt_render_region(s: *const RtScene, width: u16, height: u16, spp: u16, l: u16, b: u16, r: u16, t: u16,
                             rgba_out: *mut u8, rgba_len: usize) -> c_int;
+    pub fn rt_render_preview(s: *const RtScene, camera: *const RtCamera, width: u32, height: u32, step: u32,
+                             rgba_out: *mut u8, rgba_len: usize, stream: *mut c_void) -> c_int;
     pub fn rt_render_frame_multi(scenes: *const *mut RtScene, ngpu: c_int, camera: *const RtCamera, width: u32,
                                  height: u32, spp: u32, rgba_out: *mut u8, rgba_len: usize, stats: *mut RtStats) -> c_int;
     pub fn rt_render_sweep(s: *const RtScene, cameras: *const RtCamera, n_frames: u32, width: u32, height: u32,

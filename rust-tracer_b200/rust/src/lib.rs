@@ -92,6 +92,18 @@ impl Renderer {
         assert!(rc == 0, "render_region: {}", ffi::last_error());
     }
 
+    /// Undersampled preview (README "season 2"): one traced pixel per `step` x `step` block, 1 sample per pixel.
+    pub fn render_preview(o: &RenderOptions, scene: &Scene, writer: &mut dyn RGBABufferWriter, step: u32) {
+        writer.begin(o.width, o.height);
+        let mut frame = RGBABuffer::new(&ImageRegion { l: 0, r: o.width, b: 0, t: o.height });
+        let rc = unsafe {
+            ffi::rt_render_preview(scene.replicas[0], std::ptr::null(), o.width as u32, o.height as u32, step,
+                                   frame.buf.as_mut_ptr(), frame.buf.len(), std::ptr::null_mut())
+        };
+        assert!(rc == 0, "render_preview: {}", ffi::last_error());
+        writer.write_rgba_buffer(&frame);
+    }
+
     /// The whole frame on every GPU of the scene (rows interleaved, peer stores into GPU 0's frame).
     pub fn render(o: &RenderOptions, scene: &Scene, writer: &mut dyn RGBABufferWriter) {
         writer.begin(o.width, o.height);
