@@ -116,7 +116,9 @@ int rt_scene_device(const rt_scene *s);
  * [l,r) x [b,t) of a width x height image (b = upper image row, as in
  * ImageRegion, render.rs:43-72).  Writes (r-l)*(t-b)*4 bytes RGBA8 row-major from
  * row b (RGBABuffer layout, render.rs:69-71,92-109).  Unlike Renderer::render
- * (render.rs:264-266) sizes need not be multiples of 64. */
+ * (render.rs:264-266) sizes need not be multiples of 64.  A region narrower than
+ * the image (a bucket) is traced by the per-lane kernel over just its own pixels,
+ * so its cost is its area; a full-width region takes the variant AUTO picks. */
 int rt_render_region(const rt_scene *s, uint16_t width, uint16_t height, uint16_t spp,
                      uint16_t l, uint16_t b, uint16_t r, uint16_t t,
                      uint8_t *rgba_out, size_t rgba_len);
