@@ -104,3 +104,27 @@ def test_from_nodes_validation(rt):
         with pytest.raises(rt.RtError) as e:
             rt.Scene.from_nodes(sph, np.array(bad, np.uint32), (0, -1, 0), (0, 0, -4))
         assert e.value.code == rt.RT_ERR_INVALID
+
+
+@pytest.mark.parametrize("level", [3, 6, 8])
+def test_every_leaf_lies_two_leaf_radii_inside_each_ancestor_bound(rt, level):
+    """The candidate-list kernels replace the reference's pruned walk (group.rs:72-83) by "nearest of the leaves
+    whose exact test passes".  That is the same answer only if a bound can never prune a leaf that would have
+    won, i.e. every leaf sphere lies strictly inside each ancestor's bounding sphere with room to spare
+    against f32 noise: the pyramid (group.rs:28-56) leaves 2 x the smallest leaf radius."""
+    sph, skip = rt.flatten_pyramid_host(level)
+    n = len(skip)
+    leaf = skip == np.arange(n) + 1
+    r_min = float(sph[leaf, 3].min())
+    c64 = sph[:, :3].astype(np.float64)
+    stack, slack = [], np.inf
+    for i in range(n):
+        while stack and skip[stack[-1]] <= i:
+            stack.pop()
+        if not leaf[i]:
+            stack.append(i)
+            continue
+        anc = np.array(stack)
+        d = np.linalg.norm(c64[anc] - c64[i], axis=1) + float(sph[i, 3])
+        slack = min(slack, float((sph[anc, 3] - d).min()))
+    assert slack >= 1.99 * r_min, (slack, r_min)
