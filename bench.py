@@ -133,6 +133,23 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(rows), "reasons": reasons}
 
 
+class stdout_to_stderr:
+    """File descriptor 1 points at stderr inside the block.  NCCL prints "NCCL version ..." on stdout when the
+    first communicator is created; bench.py's stdout carries exactly one JSON line, so that goes to stderr."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def pin_to_gpu_cpus(local_rank):
     """Multi-GPU runs: keep this rank's host threads (and so its pinned frame buffers, first touch) on the
     CPUs NVML reports as local to its GPU, so that eight ranks copying frames out do not cross sockets."""
@@ -254,7 +271,9 @@ def main():
     torch.cuda.set_device(local_rank)
     rt.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        with stdout_to_stderr():   # communicator creation and the first collective: NCCL's banner
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
     rt.set_variant(args.variant)
 
     scene = rt.Scene(level=level)

@@ -35,6 +35,19 @@ def test_reference_arm_runs_on_rank_zero_only():
     assert r.returncode == 0 and r.stdout.strip() == ""
 
 
+def test_library_banners_cannot_reach_stdout():
+    """bench.py keeps stdout to one JSON line: what a library writes to fd 1 while the process group is
+    created (NCCL's version banner) lands on stderr, and stdout works again afterwards."""
+    code = ("import os, sys; sys.path.insert(0, %r); import bench\n"
+            "print('before')\n"
+            "with bench.stdout_to_stderr():\n"
+            "    os.write(1, b'banner\\n')\n"
+            "print('after')\n") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.split() == ["before", "after"] and "banner" in r.stderr
+
+
 def test_native_arm_refuses_to_run_without_a_gpu():
     import torch
     if torch.cuda.is_available():
