@@ -50,6 +50,17 @@ def test_unparsable_numbers_panic_with_101(rtrace, tmp_path):
         assert b"panicked" in r.stderr
 
 
+def test_extension_flags_are_parsed_like_the_reference_flags(rtrace, tmp_path):
+    """--preview / --level / --frames / --gpus values go through the same `.parse().unwrap()` rule
+    (main.rs:79-81): a bad number panics with 101 before any GPU work; --help lists the additions."""
+    for flag in ("--preview=abc", "--preview=5000", "--level=x", "--frames=-1", "--gpus=two"):
+        r = run(rtrace, flag, "o.tga", cwd=str(tmp_path))
+        assert r.returncode == 101 and b"panicked" in r.stderr, flag
+    assert run(rtrace, "--preview", cwd=str(tmp_path)).returncode == 1   # flag without its value: usage error
+    h = run(rtrace, "--help").stdout
+    assert b"--preview <N>" in h and b"--buckets" in h
+
+
 def test_unknown_flag_and_extra_positional_are_usage_errors(rtrace, tmp_path):
     assert run(rtrace, "--bogus", "o.tga", cwd=str(tmp_path)).returncode == 1
     assert run(rtrace, "a.tga", "b.tga", cwd=str(tmp_path)).returncode == 1
