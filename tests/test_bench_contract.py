@@ -55,3 +55,19 @@ def test_native_arm_refuses_to_run_without_a_gpu():
         pytest.skip("a GPU is present")
     r = run_bench("--steps", "1", "--warmup", "3", "--no-cpu-baseline")
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_c5_orbit_cameras_are_the_bindings_orbit_cameras():
+    """bench.py --workload c5 and --impl reference use bench.orbit_basis; the binding (and the CLI's --frames)
+    use rtrace_b200.orbit_camera.  Same f32 camera for every frame, frame 0 = the reference camera exactly."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "rust-tracer_b200"))
+    import bench
+    import rtrace_b200 as rt
+    for f in range(bench.ORBIT_FRAMES):
+        a = rt.make_camera(*bench.orbit_basis(f))
+        b = rt.orbit_camera(f, bench.ORBIT_FRAMES)
+        for name in ("eye", "right", "up", "forward"):
+            assert list(getattr(a, name)) == list(getattr(b, name)), (f, name)
+    ref = rt.make_camera(*bench.orbit_basis(0))
+    assert list(ref.eye) == [0.0, 0.0, -4.0] and list(ref.right) == [1.0, 0.0, 0.0] and list(ref.forward) == [0.0, 0.0, 1.0]
