@@ -164,8 +164,9 @@ int rt_render_frame(const rt_scene *s, const rt_camera *camera,
                     uint8_t *rgba_out, size_t rgba_len, rt_stats *stats);
 
 /* A sweep of n_frames frames (cameras[f], or the reference camera when cameras is
- * NULL) with the device-to-host copy of frame f overlapping the render of frame
- * f+1.  `cb` is called on the calling thread, in frame order, with a pinned host
+ * NULL), pipelined: two frames render at a time on two streams (the launch tails
+ * of frame f are filled by the first launches of frame f+1) while the device-to-host
+ * copy of an earlier frame runs on a third.  `cb` is called on the calling thread, in frame order, with a pinned host
  * buffer that stays valid until the callback returns.  The scene's scratch is
  * locked for the whole sweep: the callback must not render with the same scene
  * (other scenes and other threads' calls on this scene simply wait).  This is the end-to-end

@@ -52,13 +52,16 @@ struct rt_scene {
         uint32_t pool_units = 0;
         uint32_t *pool_count = nullptr;
     };
-    // rt_render_sweep: double-buffered frames and the copy stream
-    uint8_t *sweep_dev[2] = {nullptr, nullptr};
-    uint8_t *sweep_host[2] = {nullptr, nullptr};
-    uint8_t *sweep_rgb[2] = {nullptr, nullptr};
+    // rt_render_sweep: ring of frame buffers (frames rendering at a time + one being copied out), the copy
+    // stream and the second render stream
+    static constexpr int SWEEP_RING = 3;
+    uint8_t *sweep_dev[SWEEP_RING] = {nullptr, nullptr, nullptr};
+    uint8_t *sweep_host[SWEEP_RING] = {nullptr, nullptr, nullptr};
+    uint8_t *sweep_rgb[SWEEP_RING] = {nullptr, nullptr, nullptr};
     size_t sweep_bytes = 0;
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t sweep_rendered[2] = {nullptr, nullptr}, sweep_copied[2] = {nullptr, nullptr};
+    int sweep_nb = 0;  // buffers of the ring that are allocated
+    cudaStream_t copy_stream = nullptr, render2 = nullptr;
+    cudaEvent_t sweep_rendered[SWEEP_RING] = {nullptr, nullptr, nullptr}, sweep_copied[SWEEP_RING] = {nullptr, nullptr, nullptr};
     std::map<cudaStream_t, Phased> phased;
     std::mutex mu_phased;  // guards the map only (mu may already be held by the caller)
 };
@@ -418,7 +421,7 @@ void rt_scene_destroy(rt_scene *s) {
         if (s->ev0) cudaEventDestroy(s->ev0);
         if (s->ev1) cudaEventDestroy(s->ev1);
         if (s->own_stream) cudaStreamDestroy(s->own_stream);
-        for (int k = 0; k < 2; k++) {
+        for (int k = 0; k < rt_scene::SWEEP_RING; k++) {
             if (s->sweep_dev[k]) cudaFree(s->sweep_dev[k]);
             if (s->sweep_rgb[k]) cudaFree(s->sweep_rgb[k]);
             if (s->sweep_host[k]) cudaFreeHost(s->sweep_host[k]);
@@ -426,6 +429,7 @@ void rt_scene_destroy(rt_scene *s) {
             if (s->sweep_copied[k]) cudaEventDestroy(s->sweep_copied[k]);
         }
         if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+        if (s->render2) cudaStreamDestroy(s->render2);
         for (auto &kv : s->phased) {
             if (kv.second.winner) cudaFree(kv.second.winner);
             if (kv.second.hdr) cudaFree(kv.second.hdr);
@@ -705,6 +709,7 @@ static int sweep_impl(const rt_scene *cs, const rt_camera *cameras, uint32_t n_f
     rc = sweep_locked(s, cameras, n_frames, width, height, spp, cb, user, stats, rgb);
     if (rc != RT_OK) {  // leave no render or copy in flight on the double buffers (keeps the first error text)
         if (s->own_stream) cudaStreamSynchronize(s->own_stream);
+        if (s->render2) cudaStreamSynchronize(s->render2);
         if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
         cudaGetLastError();
     }
@@ -717,15 +722,25 @@ static int sweep_locked(rt_scene *s, const rt_camera *cameras, uint32_t n_frames
     const double t0 = now_ms();
     const size_t row_bytes = (size_t)width * 4, frame_bytes = row_bytes * height;
     const size_t out_bytes = rgb ? (size_t)width * height * 3 : frame_bytes;
-    // two device frames + two pinned host frames: the copy of frame f overlaps the render of f+1
-    if (s->sweep_bytes < frame_bytes) {
-        for (int k = 0; k < 2; k++) {
+    // `depth` frames render at a time, each on its own stream (depth 2: the launch tails of frame f are filled
+    // by the first launches of frame f+1), while an earlier frame is copied out: depth + 1 device frames and
+    // pinned host frames.  Measured on B200 (C5, 4K 4x4 level 9): 1.395 ms per delivered frame with one render
+    // stream, 1.294 ms with two -- less than a lone frame's 1.34 ms of kernels.  RTRACE_SWEEP_STREAMS=1 selects
+    // the single-stream schedule (kernel experiments).
+    int depth = 2;
+    if (const char *e = getenv("RTRACE_SWEEP_STREAMS")) {
+        if (*e == '1') depth = 1;
+    }
+    const int nb = depth + 1;
+    if (s->sweep_bytes < frame_bytes || s->sweep_nb < nb) {
+        for (int k = 0; k < rt_scene::SWEEP_RING; k++) {
             if (s->sweep_dev[k]) cudaFree(s->sweep_dev[k]);
             if (s->sweep_host[k]) cudaFreeHost(s->sweep_host[k]);
             s->sweep_dev[k] = s->sweep_host[k] = nullptr;
         }
         s->sweep_bytes = 0;
-        for (int k = 0; k < 2; k++) {
+        s->sweep_nb = 0;
+        for (int k = 0; k < nb; k++) {
             if (s->sweep_rgb[k]) cudaFree(s->sweep_rgb[k]);
             s->sweep_rgb[k] = nullptr;
             CUDA_TRY(cudaMalloc(&s->sweep_dev[k], frame_bytes));
@@ -733,39 +748,43 @@ static int sweep_locked(rt_scene *s, const rt_camera *cameras, uint32_t n_frames
             CUDA_TRY(cudaHostAlloc((void **)&s->sweep_host[k], frame_bytes, cudaHostAllocPortable));
         }
         s->sweep_bytes = frame_bytes;
+        s->sweep_nb = nb;
     }
+    if (depth == 2 && !s->render2) CUDA_TRY(cudaStreamCreateWithFlags(&s->render2, cudaStreamNonBlocking));
     if (!s->copy_stream) {
         CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
-        for (int k = 0; k < 2; k++) {
+        for (int k = 0; k < rt_scene::SWEEP_RING; k++) {
             CUDA_TRY(cudaEventCreateWithFlags(&s->sweep_rendered[k], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&s->sweep_copied[k], cudaEventDisableTiming));
         }
     }
     uint32_t launches = 0;
-    for (uint32_t f = 0; f <= n_frames; f++) {
+    for (uint64_t f = 0; f < (uint64_t)n_frames + (uint64_t)depth; f++) {
         if (f < n_frames) {
-            const int k = (int)(f & 1u);
+            const int k = (int)(f % (uint64_t)nb);
+            cudaStream_t rs = (depth == 2 && (f & 1u)) ? s->render2 : s->own_stream;  // PHASED scratch is per stream
             rt::RenderParams p;
             fill_params(s, cameras ? &cameras[f] : nullptr, width, height, spp, 0, 1, height, p);
             p.out = s->sweep_dev[k];
             p.pitch = row_bytes;
-            if (f >= 2) CUDA_TRY(cudaStreamWaitEvent(s->own_stream, s->sweep_copied[k], 0));  // frame f-2 has left this buffer
-            rc = launch(s, p, false, s->own_stream);
+            if (f >= (uint64_t)nb) CUDA_TRY(cudaStreamWaitEvent(rs, s->sweep_copied[k], 0));  // frame f-nb has left this buffer
+            rc = launch(s, p, false, rs);
             if (rc != RT_OK) return rc;
             launches += (uint32_t)launches_per_frame(p);
             if (rgb) {  // the sink only needs RGB: pack on the device, copy 3 bytes per pixel
-                CUDA_TRY(rt_launch_pack_rgb(s->sweep_dev[k], s->sweep_rgb[k], (size_t)width * height, s->own_stream));
+                CUDA_TRY(rt_launch_pack_rgb(s->sweep_dev[k], s->sweep_rgb[k], (size_t)width * height, rs));
                 launches += 1;
             }
-            CUDA_TRY(cudaEventRecord(s->sweep_rendered[k], s->own_stream));
+            CUDA_TRY(cudaEventRecord(s->sweep_rendered[k], rs));
             CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->sweep_rendered[k], 0));
             CUDA_TRY(cudaMemcpyAsync(s->sweep_host[k], rgb ? s->sweep_rgb[k] : s->sweep_dev[k], out_bytes, cudaMemcpyDeviceToHost, s->copy_stream));
             CUDA_TRY(cudaEventRecord(s->sweep_copied[k], s->copy_stream));
         }
-        if (f >= 1) {  // hand frame f-1 to the caller while frame f renders
-            const int k = (int)((f - 1) & 1u);
+        if (f >= (uint64_t)depth) {  // hand frame f-depth to the caller while the later ones render
+            const uint64_t done = f - (uint64_t)depth;
+            const int k = (int)(done % (uint64_t)nb);
             CUDA_TRY(cudaEventSynchronize(s->sweep_copied[k]));
-            if (cb) cb(user, f - 1, s->sweep_host[k], out_bytes);
+            if (cb) cb(user, (uint32_t)done, s->sweep_host[k], out_bytes);
         }
     }
     if (stats) {
