@@ -51,7 +51,7 @@ def from_oracle():
     # (width, height, spp, level): small parity cases + BASELINE C2 at levels 8/9/10
     for (w, h, spp, level) in [(64, 128, 2, 8), (160, 120, 1, 8), (160, 120, 3, 8), (200, 150, 4, 5), (97, 61, 2, 9),
                                (256, 144, 1, 10), (1024, 768, 1, 8), (3840, 2160, 1, 8), (3840, 2160, 1, 9),
-                               (3840, 2160, 1, 10)]:
+                               (3840, 2160, 1, 10), (3840, 2160, 4, 9)]:   # last: BASELINE C3 / C5 frame 0
         s = o.Scene(level=level)
         img, ctr = s.render(w, h, spp)
         cases.append({"width": w, "height": h, "spp": spp, "level": level,
@@ -59,7 +59,19 @@ def from_oracle():
                       "ppm_sha256": hashlib.sha256(b"P6\n%d %d\n255\n" % (w, h) + img[:, :, :3].tobytes()).hexdigest(),
                       "counters": ctr.as_dict(), "flop_per_ray": ctr.flop_per_ray()})
         print(w, h, spp, level, cases[-1]["rgba_sha256"][:16], ctr.shadow_rays)
-    json.dump({"source": "oracle/liboracle_rt.so (pinned by rtrace_output_1024x768.json)", "cases": cases},
+    # camera extension: frames of the 120-frame orbit, small enough for the CPU suite
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    import bench
+    orbit = []
+    s = o.Scene(level=8)
+    for f in (0, 7, 41, 60, 88):
+        w, h, spp = 320, 240, 2
+        img, ctr = s.render(w, h, spp, camera=o.make_camera(*bench.orbit_basis(f)))
+        orbit.append({"frame": f, "n_frames": bench.ORBIT_FRAMES, "width": w, "height": h, "spp": spp, "level": 8,
+                      "rgba_sha256": hashlib.sha256(img.tobytes()).hexdigest(), "counters": ctr.as_dict()})
+        print("orbit", f, orbit[-1]["rgba_sha256"][:16], ctr.shadow_rays)
+    json.dump({"source": "oracle/liboracle_rt.so (pinned by rtrace_output_1024x768.json)", "cases": cases,
+               "orbit_cases": orbit},
               open(os.path.join(HERE, "oracle_derived.json"), "w"), indent=1)
 
 

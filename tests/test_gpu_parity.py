@@ -70,7 +70,7 @@ def test_make_image_matches_reference_golden(rt, gpu_scene8):
     assert gpu_scene8.count_rays(w, h, spp) == (12582912, 7211901)
 
 
-@pytest.mark.parametrize("case", [c for c in DERIVED["cases"] if c["width"] == 3840],
+@pytest.mark.parametrize("case", [c for c in DERIVED["cases"] if c["width"] == 3840 and c["spp"] == 1],
                          ids=lambda c: "4k_L%d" % c["level"])
 def test_c2_4k_frames_match_oracle_fixture(rt, case):
     """BASELINE C2 (3840x2160, spp 1) at levels 8/9/10 against the committed oracle hashes."""

@@ -5,6 +5,7 @@ reference tree is mounted."""
 import hashlib
 import json
 import os
+import sys
 import zlib
 
 import numpy as np
@@ -55,6 +56,22 @@ def test_make_image_matches_reference_png_pixels(make_image):
     png = np.array(Image.open(REF_PNG).convert("RGB"))
     assert hashlib.sha256(open(REF_PNG, "rb").read()).hexdigest() == GOLD["png_sha256"]
     assert np.array_equal(png, img[:, :, :3])
+
+
+@pytest.mark.parametrize("case", DERIVED.get("orbit_cases", []), ids=lambda c: "orbit_frame_%d" % c["frame"])
+def test_oracle_orbit_fixtures(oracle, case):
+    """The camera extension (orbit about the flake's axis) as the oracle renders it: committed hashes
+    keep the oracle, bench.orbit_basis and the fixture generator in step.  Frame 0 is the reference camera."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import bench
+    s = oracle.Scene(level=case["level"])
+    cam = oracle.make_camera(*bench.orbit_basis(case["frame"], case["n_frames"]))
+    img, ctr = s.render(case["width"], case["height"], case["spp"], camera=cam)
+    assert hashlib.sha256(img.tobytes()).hexdigest() == case["rgba_sha256"]
+    assert ctr.as_dict() == case["counters"]
+    if case["frame"] == 0:
+        plain, _ = s.render(case["width"], case["height"], case["spp"])
+        assert np.array_equal(plain, img)
 
 
 @pytest.mark.parametrize("case", [c for c in DERIVED["cases"] if c["width"] * c["height"] * c["spp"] ** 2 <= 1 << 20],
