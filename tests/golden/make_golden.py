@@ -51,7 +51,8 @@ def from_oracle():
     # (width, height, spp, level): small parity cases + BASELINE C2 at levels 8/9/10
     for (w, h, spp, level) in [(64, 128, 2, 8), (160, 120, 1, 8), (160, 120, 3, 8), (200, 150, 4, 5), (97, 61, 2, 9),
                                (256, 144, 1, 10), (1024, 768, 1, 8), (3840, 2160, 1, 8), (3840, 2160, 1, 9),
-                               (3840, 2160, 1, 10), (3840, 2160, 4, 9)]:   # last: BASELINE C3 / C5 frame 0
+                               (3840, 2160, 1, 10), (3840, 2160, 4, 9), (1024, 768, 4, 8),
+                               (7680, 4320, 4, 9)]:   # last three: BASELINE C3 (= C5 frame 0), C1, C4
         s = o.Scene(level=level)
         img, ctr = s.render(w, h, spp)
         cases.append({"width": w, "height": h, "spp": spp, "level": level,
