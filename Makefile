@@ -23,7 +23,13 @@ $(LIB): $(LIBSRC) $(LIBHDR)
 	$(NVCC) $(NVFLAGS) -shared -x cu $(LIBSRC) -o $@ 2> $(PKG)/build.log || (cat $(PKG)/build.log; false)
 	@grep -E "registers|spill" $(PKG)/build.log | sort | uniq -c | sort -rn | head -20 || true
 
-rtrace: target/release/rtrace
+rtrace: target/release/rtrace target/release/rtrace_selftest
+
+# the reference's render-module tests (render.rs:437-499) for the C++ host mirror; run by tests/test_cli.py
+target/release/rtrace_selftest: $(PKG)/host/selftest.cpp $(PKG)/host/render.hpp $(LIB)
+	@mkdir -p target/release
+	$(HOSTCXX) -O2 -std=c++17 -Wall -Wextra -Iinclude -I$(PKG)/host $(PKG)/host/selftest.cpp -o $@ \
+	    -L$(PKG) -lrtrace_b200 -Wl,-rpath,'$$ORIGIN/../../$(PKG)' -pthread
 
 target/release/rtrace: $(PKG)/host/main.cpp $(PKG)/host/render.hpp $(LIB)
 	@mkdir -p target/release

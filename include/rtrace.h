@@ -60,6 +60,10 @@ typedef struct rt_stats {
     double total_ms;       /* kernel + gather + copy-out, host wall clock                   */
     uint32_t kernel_launches;
     uint32_t gpus;
+    uint32_t variant_used; /* RT_VARIANT_* the call actually ran (AUTO resolved; LANE when the arguments leave
+                              the candidate-list variants' domain: spp > 8, level > 10, eye inside the root
+                              bound, non-orthonormal camera, scene far from the coordinate origin)        */
+    uint32_t reserved;
 } rt_stats;
 
 /* Kernel variants (rt_set_variant).  All produce identical bytes. */
@@ -193,6 +197,17 @@ int rt_render_sweep_rgb(const rt_scene *s, const rt_camera *cameras, uint32_t n_
 int rt_render_frame_multi(rt_scene *const *scenes, int ngpu, const rt_camera *camera,
                           uint32_t width, uint32_t height, uint32_t spp,
                           uint8_t *rgba_out, size_t rgba_len, rt_stats *stats);
+
+/* The sweep sharded by FRAME over ngpu GPUs of this process (BASELINE configs[4]; scenes[g] is the replica
+ * on its own device, all distinct): frame f is rendered by GPU f mod ngpu through that GPU's own pipelined
+ * sweep (two frames in flight + copy-out, as rt_render_sweep) driven by its own host thread, and `cb` is
+ * called on the CALLING thread in frame order 0, 1, 2, ... with a pinned host buffer valid until it returns.
+ * rgb != 0 delivers RGB8 frames as rt_render_sweep_rgb does.  No data-path collective: frames are
+ * independent.  Replaces the one pool that takes every unit of work and the bounded channel to the writer
+ * (render.rs:271-307).  This is what `rtrace --frames K --gpus N` calls. */
+int rt_render_sweep_multi(rt_scene *const *scenes, int ngpu, const rt_camera *cameras, uint32_t n_frames,
+                          uint32_t width, uint32_t height, uint32_t spp, int rgb,
+                          rt_frame_callback cb, void *user, rt_stats *stats);
 
 /* Count rays the way the reference's work is counted: primary =
  * rows*width*spp^2, shadow = samples with a hit facing the light. */

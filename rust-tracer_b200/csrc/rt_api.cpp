@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -16,6 +17,7 @@
 #include <map>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "rt_device.cuh"
@@ -69,10 +71,15 @@ struct rt_scene {
 namespace {
 
 thread_local char g_err[512] = "";
-// rt_render_row_blocks sets these around its call into render_rows_impl (0 / false otherwise)
-thread_local uint32_t g_row_block_shift = 0;
-thread_local bool g_out_abs = false;
-thread_local int g_variant = RT_VARIANT_AUTO;
+thread_local int g_variant = RT_VARIANT_AUTO;  // rt_set_variant: the caller's choice for this thread
+
+// How the rows of a launch map to image rows and to rows of the output buffer (rt_render_row_blocks):
+// blocks of 2^block_shift consecutive image rows, row_stride apart; out_abs = rows are stored at their
+// IMAGE row of a whole frame.  The plain interleave of rt_render_rows is {0, false}.
+struct RowLayout {
+    uint32_t block_shift = 0;
+    bool out_abs = false;
+};
 
 int fail(int code, const char *fmt, ...) {
     va_list ap;
@@ -145,7 +152,7 @@ int ensure(uint8_t **buf, size_t *cap, size_t need) {
 }
 
 void fill_params(const rt_scene *s, const rt_camera *cam, uint32_t w, uint32_t h, uint32_t spp, uint32_t row_start,
-                 uint32_t row_stride, uint32_t row_count, rt::RenderParams &p) {
+                 uint32_t row_stride, uint32_t row_count, rt::RenderParams &p, RowLayout layout = RowLayout()) {
     memset(&p, 0, sizeof(p));
     p.sph = s->d_sph;
     p.skip = s->d_skip;
@@ -191,19 +198,19 @@ void fill_params(const rt_scene *s, const rt_camera *cam, uint32_t w, uint32_t h
     p.row_start = row_start;
     p.row_stride = row_stride;
     p.row_count = row_count;
-    p.row_block_shift = g_row_block_shift;
-    p.out_abs = g_out_abs ? 1 : 0;
+    p.row_block_shift = layout.block_shift;
+    p.out_abs = layout.out_abs ? 1 : 0;
 }
 
 int check_frame_args(const rt_scene *s, uint32_t w, uint32_t h, uint32_t spp, uint32_t row_start, uint32_t row_stride,
-                     uint32_t row_count) {
+                     uint32_t row_count, RowLayout layout = RowLayout()) {
     if (!s) return fail(RT_ERR_INVALID, "scene is NULL");
     // RenderOptions fields are u16 (render.rs:34-38)
     if (w == 0 || h == 0 || w > 65535u || h > 65535u || spp > 65535u)
         return fail(RT_ERR_INVALID, "width/height must be in 1..65535 and samples-per-pixel in 0..65535 (got %u x %u, spp %u)", w, h, spp);
     if (row_stride == 0) return fail(RT_ERR_INVALID, "row_stride must be >= 1");
     if (row_count > 0) {
-        const uint32_t j = row_count - 1, bs = g_row_block_shift;
+        const uint32_t j = row_count - 1, bs = layout.block_shift;
         const uint64_t last = (uint64_t)row_start + (uint64_t)(j >> bs) * row_stride + (j & ((1u << bs) - 1u));
         if (last >= h) return fail(RT_ERR_INVALID, "rows starting at %u (stride %u, blocks of %u, %u rows) leave the %u-row image", row_start, row_stride, 1u << bs, row_count, h);
         if (bs && row_stride < (1u << bs)) return fail(RT_ERR_INVALID, "row_stride %u is smaller than the row block %u", row_stride, 1u << bs);
@@ -235,9 +242,20 @@ bool eye_outside_root_bound(const rt::RenderParams &p) {
     return d2 > r * r;
 }
 
+// The conservative pre-filters of TILE / PHASED carry ABSOLUTE slacks (1e-5 on radii, 4e-6 on cone margins,
+// 0.05 pixel on image-space boxes) sized for coordinates of magnitude < 16, where one f32 ulp is < 1e-6
+// (Scene::default lies within 4.2 of the origin).  A scene or eye placed farther out has coordinate rounding
+// above those slacks, so such arguments take the per-lane walk, which has no slack to outgrow.
+bool within_analysed_range(const rt::RenderParams &p) {
+    float m = 0.0f;
+    for (int k = 0; k < 3; k++) m = fmaxf(m, fmaxf(fabsf(p.eye[k]), fabsf(p.scene_center[k]) + p.scene_radius));
+    return m <= 16.0f && p.scene_radius > 0.0f;
+}
+
 int kernel_variant(const rt::RenderParams &p) {
     if (p.col_count) return g_variant == RT_VARIANT_WARP ? RT_KERNEL_WARP : RT_KERNEL_LANE;  // bucket-sized window
-    const bool tile_ok = rt_tile_supported(p) && (!p.has_basis || orthonormal(p.basis)) && eye_outside_root_bound(p);
+    const bool tile_ok = rt_tile_supported(p) && (!p.has_basis || orthonormal(p.basis)) && eye_outside_root_bound(p) &&
+                         within_analysed_range(p);
     switch (g_variant) {
         case RT_VARIANT_LANE:
             return RT_KERNEL_LANE;
@@ -326,6 +344,8 @@ int launch(rt_scene *s, rt::RenderParams &p, bool diag, cudaStream_t stream) {
 }
 
 int launches_per_frame(const rt::RenderParams &p) { return kernel_variant(p) == RT_KERNEL_PHASED ? 4 : 1; }
+// RT_KERNEL_* and RT_VARIANT_* share their numbering (rt_kernels.h, rtrace.h)
+uint32_t variant_used(const rt::RenderParams &p) { return (uint32_t)kernel_variant(p); }
 
 }  // namespace
 
@@ -495,8 +515,8 @@ static int render_rows_impl(rt_scene *s, const rt_camera *camera, uint32_t width
                             uint32_t row_start, uint32_t row_stride, uint32_t row_count, uint8_t *rgba_out,
                             size_t pitch_bytes, uint8_t *kinds_out, cudaStream_t stream, rt_stats *stats,
                             uint64_t *count_hits, uint64_t *count_shadow, uint32_t col_start = 0,
-                            uint32_t col_count = 0) {
-    int rc = check_frame_args(s, width, height, spp, row_start, row_stride, row_count);
+                            uint32_t col_count = 0, RowLayout layout = RowLayout()) {
+    int rc = check_frame_args(s, width, height, spp, row_start, row_stride, row_count, layout);
     if (rc != RT_OK) return rc;
     const bool counting = count_shadow != nullptr;
     if (!rgba_out && !counting) return fail(RT_ERR_INVALID, "rgba_out is NULL");
@@ -529,13 +549,13 @@ static int render_rows_impl(rt_scene *s, const rt_camera *camera, uint32_t width
     const bool kinds_on_device = kinds_out && is_device_ptr(kinds_out, &kinds_dev);
     const size_t kinds_bytes = (size_t)cols * row_count * spp * spp;
 
-    if (g_out_abs && !out_on_device) return fail(RT_ERR_INVALID, "absolute row addressing needs a device (or peer) frame buffer");
+    if (layout.out_abs && !out_on_device) return fail(RT_ERR_INVALID, "absolute row addressing needs a device (or peer) frame buffer");
     const bool need_lock = !out_on_device || (kinds_out && !kinds_on_device) || counting || stats;
     std::unique_lock<std::mutex> lock(s->mu, std::defer_lock);
     if (need_lock) lock.lock();
 
     rt::RenderParams p;
-    fill_params(s, camera, width, height, spp, row_start, row_stride, row_count, p);
+    fill_params(s, camera, width, height, spp, row_start, row_stride, row_count, p, layout);
     p.col_start = col_count ? col_start : 0;
     p.col_count = col_count;
     if (out_on_device) {
@@ -602,6 +622,7 @@ static int render_rows_impl(rt_scene *s, const rt_camera *camera, uint32_t width
         stats->shadow_rays = counting ? ctr[1] : 0;
         stats->kernel_launches = (uint32_t)launches_per_frame(p);
         stats->gpus = 1;
+        stats->variant_used = variant_used(p);
     }
     return RT_OK;
 }
@@ -619,13 +640,11 @@ int rt_render_row_blocks(const rt_scene *s, const rt_camera *camera, uint32_t wi
     if (row_block == 0 || (row_block & (row_block - 1u)) || row_block > 32768u) return fail(RT_ERR_INVALID, "row_block must be a power of two (got %u)", row_block);
     uint32_t shift = 0;
     while ((1u << shift) < row_block) shift++;
-    g_row_block_shift = shift;
-    g_out_abs = absolute_rows != 0;
-    int rc = render_rows_impl(const_cast<rt_scene *>(s), camera, width, height, spp, row_start, row_stride, row_count,
-                              rgba_out, pitch_bytes, nullptr, (cudaStream_t)stream, stats, nullptr, nullptr);
-    g_row_block_shift = 0;
-    g_out_abs = false;
-    return rc;
+    RowLayout layout;
+    layout.block_shift = shift;
+    layout.out_abs = absolute_rows != 0;
+    return render_rows_impl(const_cast<rt_scene *>(s), camera, width, height, spp, row_start, row_stride, row_count,
+                            rgba_out, pitch_bytes, nullptr, (cudaStream_t)stream, stats, nullptr, nullptr, 0, 0, layout);
 }
 
 int rt_render_region(const rt_scene *s, uint16_t width, uint16_t height, uint16_t spp, uint16_t l, uint16_t b,
@@ -758,7 +777,7 @@ static int sweep_locked(rt_scene *s, const rt_camera *cameras, uint32_t n_frames
             CUDA_TRY(cudaEventCreateWithFlags(&s->sweep_copied[k], cudaEventDisableTiming));
         }
     }
-    uint32_t launches = 0;
+    uint32_t launches = 0, used = 0;
     for (uint64_t f = 0; f < (uint64_t)n_frames + (uint64_t)depth; f++) {
         if (f < n_frames) {
             const int k = (int)(f % (uint64_t)nb);
@@ -771,6 +790,7 @@ static int sweep_locked(rt_scene *s, const rt_camera *cameras, uint32_t n_frames
             rc = launch(s, p, false, rs);
             if (rc != RT_OK) return rc;
             launches += (uint32_t)launches_per_frame(p);
+            used = variant_used(p);
             if (rgb) {  // the sink only needs RGB: pack on the device, copy 3 bytes per pixel
                 CUDA_TRY(rt_launch_pack_rgb(s->sweep_dev[k], s->sweep_rgb[k], (size_t)width * height, rs));
                 launches += 1;
@@ -792,6 +812,7 @@ static int sweep_locked(rt_scene *s, const rt_camera *cameras, uint32_t n_frames
         stats->primary_rays = (uint64_t)width * height * spp * spp * n_frames;
         stats->kernel_launches = launches;
         stats->gpus = 1;
+        stats->variant_used = used;
     }
     return RT_OK;
 }
@@ -806,24 +827,13 @@ int rt_render_sweep_rgb(const rt_scene *s, const rt_camera *cameras, uint32_t n_
     return sweep_impl(s, cameras, n_frames, width, height, spp, cb, user, stats, true);
 }
 
-int rt_render_frame_multi(rt_scene *const *scenes, int ngpu, const rt_camera *camera, uint32_t width, uint32_t height,
-                          uint32_t spp, uint8_t *rgba_out, size_t rgba_len, rt_stats *stats) {
-    if (!scenes || ngpu < 1) return fail(RT_ERR_INVALID, "need at least one scene");
-    if (!rgba_out) return fail(RT_ERR_INVALID, "rgba_out is NULL");
-    if (rgba_len < (size_t)width * height * 4) return fail(RT_ERR_BUFFER, "rgba_out holds %zu bytes, frame needs %zu", rgba_len, (size_t)width * height * 4);
-    for (int g = 0; g < ngpu; g++) {
-        int rc = check_frame_args(scenes[g], width, height, spp, 0, 1, height);
-        if (rc != RT_OK) return rc;
-    }
-    if (stats) memset(stats, 0, sizeof(*stats));
-    if (ngpu == 1) return rt_render_frame(scenes[0], camera, width, height, spp, rgba_out, rgba_len, stats);
-
+// Body of rt_render_frame_multi once every scene's scratch is locked.  `launched` records the GPUs that have
+// work in flight, so that the caller can drain them whatever happens here.
+static int frame_multi_locked(rt_scene *const *scenes, int ngpu, const rt_camera *camera, uint32_t width, uint32_t height,
+                              uint32_t spp, uint8_t *rgba_out, rt_stats *stats, std::vector<char> &launched) {
     const double t0 = now_ms();
     const size_t row_bytes = (size_t)width * 4;
     rt_scene *root = scenes[0];
-    std::vector<std::unique_lock<std::mutex>> locks;
-    for (int g = 0; g < ngpu; g++) locks.emplace_back(scenes[g]->mu);
-
     // The gathered frame lives on GPU 0; GPU 0's own band is rendered straight into it.
     {
         DeviceGuard guard(root->device);
@@ -831,8 +841,7 @@ int rt_render_frame_multi(rt_scene *const *scenes, int ngpu, const rt_camera *ca
         if (rc != RT_OK) return rc;
     }
     uint8_t *frame = root->d_frame;
-    std::vector<char> launched((size_t)ngpu, 0);  // GPUs whose share of the rows is not empty
-    uint32_t launches = 0;
+    uint32_t launches = 0, used = 0;
     for (int g = 0; g < ngpu; g++) {
         rt_scene *s = scenes[g];
         DeviceGuard guard(s->device);
@@ -857,11 +866,10 @@ int rt_render_frame_multi(rt_scene *const *scenes, int ngpu, const rt_camera *ca
             rows = 0;
             for (uint64_t y0 = first; y0 < height; y0 += stride) rows += (uint32_t)std::min<uint64_t>(B, height - y0);
             if (rows == 0) continue;
-            g_row_block_shift = 4;
-            g_out_abs = true;
-            fill_params(s, camera, width, height, spp, first, stride, rows, p);
-            g_row_block_shift = 0;
-            g_out_abs = false;
+            RowLayout layout;
+            layout.block_shift = 4;
+            layout.out_abs = true;
+            fill_params(s, camera, width, height, spp, first, stride, rows, p, layout);
             p.out = frame;
             p.pitch = row_bytes;
         } else {
@@ -874,12 +882,13 @@ int rt_render_frame_multi(rt_scene *const *scenes, int ngpu, const rt_camera *ca
             p.pitch = row_bytes;
         }
         if (stats) CUDA_TRY(cudaEventRecord(s->ev0, s->own_stream));
+        launched[(size_t)g] = 1;  // from here on this GPU may have work in flight
         {
             int rc = launch(s, p, false, s->own_stream);
             if (rc != RT_OK) return rc;
         }
-        launched[(size_t)g] = 1;
         launches += (uint32_t)launches_per_frame(p);
+        if (g == 0) used = variant_used(p);
         if (stats) CUDA_TRY(cudaEventRecord(s->ev1, s->own_stream));
         if (!peer)  // no peer access: strided copy, the pitch de-interleaves the band into the frame
             CUDA_TRY(cudaMemcpy2DAsync(frame + row_bytes * g, row_bytes * ngpu, s->d_fb, row_bytes, row_bytes, rows, cudaMemcpyDefault, s->own_stream));
@@ -905,6 +914,171 @@ int rt_render_frame_multi(rt_scene *const *scenes, int ngpu, const rt_camera *ca
         stats->primary_rays = (uint64_t)width * height * spp * spp;
         stats->kernel_launches = launches;
         stats->gpus = (uint32_t)ngpu;
+        stats->variant_used = used;
+    }
+    return RT_OK;
+}
+
+// Distinct scenes, locked in address order (two threads passing the same scenes in different orders cannot
+// deadlock; the same scene twice would lock one mutex twice, so it is rejected).
+static int lock_scenes(rt_scene *const *scenes, int ngpu, std::vector<std::unique_lock<std::mutex>> &locks) {
+    std::vector<rt_scene *> order(scenes, scenes + ngpu);
+    std::sort(order.begin(), order.end());
+    for (int g = 1; g < ngpu; g++)
+        if (order[(size_t)g] == order[(size_t)g - 1]) return fail(RT_ERR_INVALID, "the same scene was passed twice: one replica per GPU is needed");
+    for (int g = 0; g < ngpu; g++) locks.emplace_back(order[(size_t)g]->mu);
+    return RT_OK;
+}
+
+int rt_render_frame_multi(rt_scene *const *scenes, int ngpu, const rt_camera *camera, uint32_t width, uint32_t height,
+                          uint32_t spp, uint8_t *rgba_out, size_t rgba_len, rt_stats *stats) {
+    if (!scenes || ngpu < 1) return fail(RT_ERR_INVALID, "need at least one scene");
+    if (!rgba_out) return fail(RT_ERR_INVALID, "rgba_out is NULL");
+    if (rgba_len < (size_t)width * height * 4) return fail(RT_ERR_BUFFER, "rgba_out holds %zu bytes, frame needs %zu", rgba_len, (size_t)width * height * 4);
+    for (int g = 0; g < ngpu; g++) {
+        int rc = check_frame_args(scenes[g], width, height, spp, 0, 1, height);
+        if (rc != RT_OK) return rc;
+    }
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (ngpu == 1) return rt_render_frame(scenes[0], camera, width, height, spp, rgba_out, rgba_len, stats);
+
+    std::vector<std::unique_lock<std::mutex>> locks;
+    int rc = lock_scenes(scenes, ngpu, locks);
+    if (rc != RT_OK) return rc;
+    std::vector<char> launched((size_t)ngpu, 0);  // GPUs whose share of the rows is not empty
+    rc = frame_multi_locked(scenes, ngpu, camera, width, height, spp, rgba_out, stats, launched);
+    if (rc != RT_OK) {
+        // Kernels already launched on other GPUs may still be storing into GPU 0's frame through peer memory:
+        // drain every GPU before the locks are released (a later call may free or reuse that frame).  Keeps
+        // the first error text.
+        for (int g = 0; g < ngpu; g++) {
+            if (!launched[(size_t)g]) continue;
+            DeviceGuard guard(scenes[g]->device);
+            cudaStreamSynchronize(scenes[g]->own_stream);
+        }
+        cudaGetLastError();
+    }
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
+// Frame-sharded sweep over the GPUs of this process (BASELINE configs[4])
+// ---------------------------------------------------------------------------
+// The reference has ONE scheduler that owns every unit of work and a consumer that takes the results as they
+// come (render.rs:271-307: pool.execute per bucket, sync_channel(4), the main thread draining into the
+// writer).  Here the unit is a frame: frame f goes to GPU f mod N, every GPU runs the pipelined single-GPU
+// sweep over its own frames on its own host thread (launches of the GPUs never queue behind one another), and
+// the calling thread hands the frames to `cb` in frame order -- a worker blocks in its hand-over until the
+// caller has returned from the callback, because the pinned buffer is only valid that long; that is the
+// bounded channel.
+}  // extern "C"
+
+namespace {
+
+struct SweepShare {
+    // hand-over slot of one GPU's worker thread
+    std::mutex mu;
+    std::condition_variable cv;
+    bool ready = false, consumed = false, finished = false, abort = false;
+    uint32_t frame = 0;
+    const uint8_t *data = nullptr;
+    size_t len = 0;
+    int rc = RT_OK;
+    char err[512] = "";
+    rt_stats stats;
+    uint32_t stride = 1, offset = 0;  // this GPU renders global frames offset, offset + stride, ...
+};
+
+void sweep_share_callback(void *user, uint32_t local_frame, const uint8_t *data, size_t len) {
+    SweepShare *sh = static_cast<SweepShare *>(user);
+    std::unique_lock<std::mutex> lock(sh->mu);
+    if (sh->abort) return;  // the caller gave up: let this GPU's pipeline run dry without hand-overs
+    sh->frame = sh->offset + local_frame * sh->stride;
+    sh->data = data;
+    sh->len = len;
+    sh->consumed = false;
+    sh->ready = true;
+    sh->cv.notify_all();
+    sh->cv.wait(lock, [&] { return sh->consumed || sh->abort; });
+    sh->ready = false;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rt_render_sweep_multi(rt_scene *const *scenes, int ngpu, const rt_camera *cameras, uint32_t n_frames, uint32_t width,
+                          uint32_t height, uint32_t spp, int rgb, rt_frame_callback cb, void *user, rt_stats *stats) {
+    if (!scenes || ngpu < 1) return fail(RT_ERR_INVALID, "need at least one scene");
+    for (int g = 0; g < ngpu; g++) {
+        int rc = check_frame_args(scenes[g], width, height, spp, 0, 1, height);
+        if (rc != RT_OK) return rc;
+    }
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (n_frames == 0) return RT_OK;
+    if (ngpu == 1) return sweep_impl(scenes[0], cameras, n_frames, width, height, spp, cb, user, stats, rgb != 0);
+    {   // distinct scenes (each worker locks its own)
+        std::vector<rt_scene *> order(scenes, scenes + ngpu);
+        std::sort(order.begin(), order.end());
+        for (int g = 1; g < ngpu; g++)
+            if (order[(size_t)g] == order[(size_t)g - 1]) return fail(RT_ERR_INVALID, "the same scene was passed twice: one replica per GPU is needed");
+    }
+    const double t0 = now_ms();
+    const int variant = g_variant;  // the caller's choice travels to the workers (it is thread-local)
+    std::vector<SweepShare> share((size_t)ngpu);
+    std::vector<std::vector<rt_camera>> cams((size_t)ngpu);
+    std::vector<std::thread> workers;
+    for (int g = 0; g < ngpu; g++) {
+        SweepShare &sh = share[(size_t)g];
+        sh.stride = (uint32_t)ngpu;
+        sh.offset = (uint32_t)g;
+        memset(&sh.stats, 0, sizeof(sh.stats));
+        const uint32_t mine = n_frames > (uint32_t)g ? (n_frames - (uint32_t)g + (uint32_t)ngpu - 1) / (uint32_t)ngpu : 0;
+        if (cameras)
+            for (uint32_t i = 0; i < mine; i++) cams[(size_t)g].push_back(cameras[(size_t)g + (size_t)i * ngpu]);
+        workers.emplace_back([&, g, mine, variant]() {
+            SweepShare &me = share[(size_t)g];
+            g_variant = variant;
+            int rc = RT_OK;
+            if (mine) rc = sweep_impl(scenes[g], cameras ? cams[(size_t)g].data() : nullptr, mine, width, height, spp, sweep_share_callback, &me, &me.stats, rgb != 0);
+            std::lock_guard<std::mutex> lock(me.mu);
+            me.rc = rc;
+            if (rc != RT_OK) snprintf(me.err, sizeof(me.err), "GPU %d: %s", scenes[g]->device, g_err);
+            me.finished = true;
+            me.cv.notify_all();
+        });
+    }
+    int rc = RT_OK;
+    char err[512] = "";
+    for (uint32_t f = 0; f < n_frames && rc == RT_OK; f++) {
+        SweepShare &sh = share[(size_t)(f % (uint32_t)ngpu)];
+        std::unique_lock<std::mutex> lock(sh.mu);
+        sh.cv.wait(lock, [&] { return (sh.ready && sh.frame == f) || sh.finished; });
+        if (!(sh.ready && sh.frame == f)) {  // the worker ended before delivering frame f
+            rc = sh.rc != RT_OK ? sh.rc : RT_ERR_CUDA;
+            snprintf(err, sizeof(err), "%s", sh.rc != RT_OK ? sh.err : "sweep worker ended early");
+            break;
+        }
+        if (cb) cb(user, f, sh.data, sh.len);
+        sh.consumed = true;
+        sh.cv.notify_all();
+    }
+    if (rc != RT_OK)
+        for (SweepShare &sh : share) {
+            std::lock_guard<std::mutex> lock(sh.mu);
+            sh.abort = true;
+            sh.cv.notify_all();
+        }
+    for (std::thread &t : workers) t.join();
+    for (SweepShare &sh : share)
+        if (rc == RT_OK && sh.rc != RT_OK) rc = sh.rc, snprintf(err, sizeof(err), "%s", sh.err);
+    if (rc != RT_OK) return fail(rc, "%s", err);
+    if (stats) {
+        stats->total_ms = now_ms() - t0;
+        stats->primary_rays = (uint64_t)width * height * spp * spp * n_frames;
+        for (SweepShare &sh : share) stats->kernel_launches += sh.stats.kernel_launches;
+        stats->gpus = (uint32_t)ngpu;
+        stats->variant_used = share[0].stats.variant_used;
     }
     return RT_OK;
 }

@@ -154,10 +154,13 @@ static constexpr uint32_t SU = 3;  // 16-byte units per shadow candidate record
 // rays that can hit (screen_box), and the candidate's disc in the plane perpendicular to the light.
 RT_DEV uint32_t flush_reserve(const RenderParams &p, int lane, uint32_t n, uint32_t rec_units, uint32_t head, bool &ok) {
     const uint32_t units = 1u + rec_units * n;
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(p.pool_count, units);
+    // Once the pool is exhausted the counter stops growing: a warp that reads a value past the capacity does
+    // not add to it, so it stays below pool_cap + (resident warps x one reservation) and can never wrap past
+    // 2^32 and hand out units that alias live chunks (pool_cap <= 2^26).  The comparison is 64-bit.
+    uint32_t base = 0xffffffffu;
+    if (lane == 0 && *reinterpret_cast<volatile uint32_t *>(p.pool_count) <= p.pool_cap) base = atomicAdd(p.pool_count, units);
     base = __shfl_sync(FULLMASK, base, 0);
-    ok = base + units <= p.pool_cap;
+    ok = (uint64_t)base + units <= (uint64_t)p.pool_cap;
     if (ok && lane == 0) p.pool[base] = make_uint4(n, head, 0u, 0u);
     return base;
 }

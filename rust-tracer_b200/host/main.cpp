@@ -10,8 +10,8 @@
 // image` keeps working; they size the reference's CPU thread pool, which no
 // longer exists -- the GPU path ignores them.
 // Additive flags: --level=L (scene depth, default 8 as at render.rs:147),
-// --gpus=N / RTRACE_GPUS (default 1), --frames=K (orbit sweep; frame f goes to
-// <stem>.f.tga, frame 0 is the reference camera), --stats (summary on stderr), --buckets (the reference's 64x64 bucket
+// --gpus=N / RTRACE_GPUS (default 1: one frame = interleaved row blocks over the GPUs; a sweep = frame f on
+// GPU f mod N), --frames=K (orbit sweep; frame f goes to <stem>.f.tga, frame 0 is the reference camera), --stats (summary on stderr), --buckets (the reference's 64x64 bucket
 // schedule through Renderer::render_region instead of one launch per frame).
 #include <cerrno>
 #include <chrono>
@@ -50,7 +50,8 @@ const char *USAGE =
     "        --samples-per-pixel <SAMPLES>      Amount of samples per pixel. 4 means 16 over-samples [default: 1]\n"
     "        --width <X>                        The width of the output image [default: 1024]\n"
     "        --level <L>                        Depth of the sphere pyramid [default: 8]\n"
-    "        --gpus <N>                         GPUs to render on; rows are interleaved [default: 1 or RTRACE_GPUS]\n"
+    "        --gpus <N>                         GPUs to render on: a frame is split into interleaved row blocks,\n"
+    "                                           a sweep (--frames) into whole frames [default: 1 or RTRACE_GPUS]\n"
     "        --frames <K>                       Render a K-frame orbit of the camera [default: 1]\n"
     "        --format <ppm|tga>                 File contents: the reference's binary PPM, or a real TGA [default: ppm]\n"
     "        --preview <N>                      Undersampled preview: trace one pixel per NxN block (1 sample) [default: off]\n"
@@ -263,8 +264,9 @@ int main(int argc, char **argv) {
             if (!fp) throw Panic(std::string("called `Result::unwrap()` on an `Err` value: ") + strerror(errno));
             return FileOrAnyWriter::file_writer(fp);
         };
-        if (frames > 1 && gpus == 1 && !preview && !args.buckets) {
-            // orbit sweep on one GPU: copy-out of frame f overlaps the render of frame f+1
+        if (frames > 1 && !preview && !args.buckets) {
+            // orbit sweep: frame f on GPU f mod N, copy-out of a frame overlapping the render of the next ones;
+            // the frames come back in order (rt_render_sweep_multi)
             std::vector<rt_camera> cams;
             for (unsigned f = 0; f < frames; f++) cams.push_back(orbit_camera(f, frames));
             rt_stats st;

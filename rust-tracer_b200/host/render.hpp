@@ -13,10 +13,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <memory>
 #include <unistd.h>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "rtrace.h"
@@ -322,23 +324,33 @@ struct Renderer {
             }
     }
 
-    // A sweep of frames on one GPU (extension): the device-to-host copy of frame f overlaps the
-    // render of frame f+1 (rt_render_sweep).  `sink(f, bytes, len)` is called once per frame, in order;
-    // with rgb = true the frames arrive as RGB8 (the body of the P6 file, alpha already dropped).
+    // A sweep of frames (extension; BASELINE configs[4]): frame f goes to GPU f mod N, every GPU pipelines its
+    // own frames (copy-out of one frame overlapping the render of the next two), and `sink(f, bytes, len)` is
+    // called once per frame, in frame order, on the calling thread -- the role of the reference's main thread
+    // draining the channel into the writer (render.rs:301-307).  With rgb = true the frames arrive as RGB8
+    // (the body of the P6 file, alpha already dropped).  An exception thrown by the sink does not cross the C
+    // boundary: it is caught in the trampoline, the remaining frames are skipped, and it is rethrown here once
+    // the sweep has returned (no render or copy is left in flight on the library's buffers).
     template <class Sink>
     static void render_sweep(const RenderOptions &o, const Scene &scene, const std::vector<rt_camera> &cameras,
                              Sink &&sink, rt_stats *stats = nullptr, bool rgb = false) {
         struct Ctx {
-            Sink *sink;
-            const RenderOptions *o;
-        } ctx{&sink, &o};
+            typename std::remove_reference<Sink>::type *sink;
+            std::exception_ptr error;
+        } ctx{&sink, nullptr};
         auto trampoline = [](void *user, uint32_t frame, const uint8_t *rgba, size_t len) {
             Ctx *c = static_cast<Ctx *>(user);
-            (*c->sink)(frame, rgba, len);
+            if (c->error) return;  // a previous frame's sink failed: drain quietly
+            try {
+                (*c->sink)(frame, rgba, len);
+            } catch (...) {
+                c->error = std::current_exception();
+            }
         };
-        rt_check((rgb ? rt_render_sweep_rgb : rt_render_sweep)(scene.replicas()[0], cameras.data(), (uint32_t)cameras.size(),
-                                                               o.width, o.height, o.samples_per_pixel, trampoline, &ctx, stats),
-                 "Renderer::render_sweep");
+        const int rc = rt_render_sweep_multi(scene.replicas(), scene.gpus(), cameras.data(), (uint32_t)cameras.size(), o.width,
+                                             o.height, o.samples_per_pixel, rgb ? 1 : 0, trampoline, &ctx, stats);
+        if (ctx.error) std::rethrow_exception(ctx.error);
+        rt_check(rc, "Renderer::render_sweep");
     }
 };
 

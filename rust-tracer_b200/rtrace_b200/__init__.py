@@ -15,7 +15,7 @@ PKG_DIR = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("RTRACE_B200_LIB") or os.path.join(PKG_DIR, "librtrace_b200.so")  # env: kernel experiments
 
 RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_NOMEM, RT_ERR_BUFFER = 0, -1, -2, -3, -4
-VARIANT_AUTO, VARIANT_LANE, VARIANT_WARP, VARIANT_TILE, VARIANT_PHASED = 0, 1, 2, 3, 4
+VARIANT_AUTO, VARIANT_LANE, VARIANT_WARP, VARIANT_TILE, VARIANT_PHASED, VARIANT_PIPE = 0, 1, 2, 3, 4, 5
 
 # every symbol include/rtrace.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "rt_scene_create", "rt_scene_create_default", "rt_scene_create_from_nodes", "rt_scene_destroy",
     "rt_scene_counts", "rt_scene_export_nodes", "rt_flatten_pyramid_host", "rt_scene_light", "rt_scene_eye",
     "rt_scene_device", "rt_render_region", "rt_render_preview", "rt_render_rows", "rt_render_row_blocks", "rt_render_frame", "rt_render_sweep", "rt_render_sweep_rgb",
-    "rt_render_frame_multi",
+    "rt_render_frame_multi", "rt_render_sweep_multi",
     "rt_count_rays", "rt_trace_rays", "rt_measure_fp32_peak", "rt_microbench_fp32", "rt_selftest_math", "rt_debug_phased_tiles", "rt_host_alloc", "rt_host_free", "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_memcpy",
 ]
 
@@ -40,7 +40,8 @@ class Camera(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("primary_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("kernel_ms", C.c_double),
-                ("total_ms", C.c_double), ("kernel_launches", C.c_uint32), ("gpus", C.c_uint32)]
+                ("total_ms", C.c_double), ("kernel_launches", C.c_uint32), ("gpus", C.c_uint32),
+                ("variant_used", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 FRAME_CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint8), C.c_size_t)
@@ -85,6 +86,8 @@ def lib():
     L.rt_render_sweep_rgb.argtypes = L.rt_render_sweep.argtypes
     L.rt_render_frame_multi.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(Camera), u32, u32, u32, u8p, C.c_size_t,
                                         C.POINTER(Stats)]
+    L.rt_render_sweep_multi.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(Camera), u32, u32, u32, u32, C.c_int,
+                                        FRAME_CALLBACK, vp, C.POINTER(Stats)]
     L.rt_count_rays.argtypes = [vp, C.POINTER(Camera), u32, u32, u32, u32, u32, u32, u64p, u64p]
     L.rt_trace_rays.argtypes = [vp, C.c_size_t, vp, vp]
     L.rt_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -343,6 +346,24 @@ class Renderer:
         st = Stats()
         fn = lib().rt_render_sweep_rgb if rgb else lib().rt_render_sweep
         _check(fn(scene.handle, cams, n_frames, w, h, spp, cb, None, C.byref(st)))
+        return st
+
+    @staticmethod
+    def render_sweep_multi(options, scenes, n_frames, cameras=None, on_frame=None, rgb=False):
+        """The sweep sharded by frame over len(scenes) GPUs of this process (frame f on GPU f mod N);
+        on_frame(f, array) is called in frame order on the calling thread."""
+        w, h, spp = options.width, options.height, options.samples_per_pixel
+        cams = (Camera * n_frames)(*cameras) if cameras is not None else None
+
+        def _cb(user, frame, ptr, nbytes):
+            if on_frame is not None:
+                on_frame(int(frame), np.ctypeslib.as_array(ptr, shape=(h, w, 3 if rgb else 4)))
+
+        cb = FRAME_CALLBACK(_cb)
+        st = Stats()
+        arr = (C.c_void_p * len(scenes))(*[s.handle for s in scenes])
+        _check(lib().rt_render_sweep_multi(arr, len(scenes), cams, n_frames, w, h, spp, 1 if rgb else 0, cb, None,
+                                           C.byref(st)))
         return st
 
     @staticmethod

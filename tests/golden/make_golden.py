@@ -72,10 +72,35 @@ def from_oracle():
                       "rgba_sha256": hashlib.sha256(img.tobytes()).hexdigest(), "counters": ctr.as_dict()})
         print("orbit", f, orbit[-1]["rgba_sha256"][:16], ctr.shadow_rays)
     json.dump({"source": "oracle/liboracle_rt.so (pinned by rtrace_output_1024x768.json)", "cases": cases,
-               "orbit_cases": orbit},
+               "orbit_cases": orbit, "c5_cases": c5_frames()},
               open(os.path.join(HERE, "oracle_derived.json"), "w"), indent=1)
 
 
+def c5_frames(frames=(7, 41, 88)):
+    """BASELINE configs[4] at REAL size: orbit frames of the 120-frame sweep at 3840x2160, 4x4 samples,
+    level 9 (87,381 spheres).  Frame 0 is the C3 case above (the reference camera)."""
+    import _oracle as o
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    import bench
+    s = o.Scene(level=9)
+    out = []
+    for f in frames:
+        w, h, spp = 3840, 2160, 4
+        img, ctr = s.render(w, h, spp, camera=o.make_camera(*bench.orbit_basis(f)))
+        out.append({"frame": f, "n_frames": bench.ORBIT_FRAMES, "width": w, "height": h, "spp": spp, "level": 9,
+                    "rgba_sha256": hashlib.sha256(img.tobytes()).hexdigest(),
+                    "rgb_sha256": hashlib.sha256(np.ascontiguousarray(img[:, :, :3]).tobytes()).hexdigest(),
+                    "counters": ctr.as_dict(), "flop_per_ray": ctr.flop_per_ray()})
+        print("c5 frame", f, out[-1]["rgba_sha256"][:16], ctr.shadow_rays)
+    return out
+
+
 if __name__ == "__main__":
-    from_reference_png()
-    from_oracle()
+    if "--only-c5" in sys.argv:   # add / refresh the real-size C5 frames without re-rendering the rest
+        path = os.path.join(HERE, "oracle_derived.json")
+        d = json.load(open(path))
+        d["c5_cases"] = c5_frames()
+        json.dump(d, open(path, "w"), indent=1)
+    else:
+        from_reference_png()
+        from_oracle()

@@ -168,3 +168,67 @@ def test_real_tga_output_holds_the_same_pixels(rtrace, tmp_path):
     # the sweep path writes the same format
     r = run(rtrace, "--width=%d" % w, "--height=%d" % h, "--samples-per-pixel=2", "--format=tga", "--frames=2", "s.tga", cwd=str(tmp_path))
     assert r.returncode == 0 and (tmp_path / "s.0000.tga").read_bytes() == data
+
+
+SELFTEST = os.path.join(ROOT, "target", "release", "rtrace_selftest")
+
+
+def selftest(rtrace, *args):
+    assert os.path.exists(SELFTEST), "make rtrace builds target/release/rtrace_selftest"
+    return subprocess.run([SELFTEST] + list(args), capture_output=True, timeout=120)
+
+
+def test_image_region_kat(rtrace):
+    """render.rs:483-499 `image_region`, value for value, on the C++ mirror of ImageRegion (no GPU needed)."""
+    r = selftest(rtrace, "image_region")
+    assert r.returncode == 0 and b"ok image_region" in r.stdout, r.stderr
+
+
+@pytest.mark.gpu
+def test_writer_seam_kat_basic_rendering(rtrace):
+    """render.rs:466-481 `basic_rendering`: 64x128, 2x2 samples, a counting DummyWriter sees begin() and exactly
+    two bucket writes when the frame goes through the reference's 64x64 schedule (Renderer::render_buckets)."""
+    r = selftest(rtrace, "basic_rendering")
+    assert r.returncode == 0 and b"ok basic_rendering" in r.stdout, r.stderr
+
+
+@pytest.mark.gpu
+def test_progressive_rewrite_once_per_second(rtrace, tmp_path):
+    """render.rs:426-432: a file sink rewrites the whole image on the first buffer and then at most once per
+    second; the drop writes the final image (render.rs:331-335); a non-file sink writes only on drop."""
+    r = selftest(rtrace, "progressive", str(tmp_path / "p.tga"))
+    assert r.returncode == 0 and b"ok progressive" in r.stdout, r.stderr
+
+
+@pytest.mark.gpu
+def test_sink_exception_does_not_cross_the_c_boundary(rtrace):
+    r = selftest(rtrace, "sink_error")
+    assert r.returncode == 0 and b"ok sink_error" in r.stdout, r.stderr
+
+
+def _gpus():
+    import rtrace_b200 as rt
+    return rt.device_count()
+
+
+@pytest.mark.gpu
+def test_two_gpu_frame_and_sweep_write_the_same_files(rtrace, tmp_path):
+    """`--gpus 2`: one frame split into interleaved row blocks (rt_render_frame_multi) and a sweep sharded by
+    frame (rt_render_sweep_multi) write exactly the files one GPU writes."""
+    if _gpus() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    one = run(rtrace, "--width=320", "--height=200", "--samples-per-pixel=2", "-")
+    two = run(rtrace, "--width=320", "--height=200", "--samples-per-pixel=2", "--gpus=2", "--stats", "-")
+    assert one.returncode == 0 and two.returncode == 0, two.stderr
+    assert one.stdout == two.stdout and b"on 2 GPU(s)" in two.stderr
+    a = run(rtrace, "--width=160", "--height=96", "--frames=5", "a.tga", cwd=str(tmp_path))
+    b = run(rtrace, "--width=160", "--height=96", "--frames=5", "--gpus=2", "b.tga", cwd=str(tmp_path),
+            env={"RTRACE_GPUS": "1"})   # the flag overrides the environment
+    assert a.returncode == 0 and b.returncode == 0, b.stderr
+    for f in range(5):
+        assert (tmp_path / ("a.%04d.tga" % f)).read_bytes() == (tmp_path / ("b.%04d.tga" % f)).read_bytes(), f
+    # `make image` on two GPUs is still the reference's golden file
+    r = run(rtrace, "--samples-per-pixel=4", "--width=1024", "--height=768", "out.tga", cwd=str(tmp_path),
+            env={"RTRACE_GPUS": "2"})
+    assert r.returncode == 0, r.stderr
+    assert hashlib.sha256((tmp_path / "out.tga").read_bytes()).hexdigest() == GOLD["ppm_sha256"]

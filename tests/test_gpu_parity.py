@@ -70,15 +70,39 @@ def test_make_image_matches_reference_golden(rt, gpu_scene8):
     assert gpu_scene8.count_rays(w, h, spp) == (12582912, 7211901)
 
 
-@pytest.mark.parametrize("case", [c for c in DERIVED["cases"] if c["width"] == 3840 and c["spp"] == 1],
-                         ids=lambda c: "4k_L%d" % c["level"])
-def test_c2_4k_frames_match_oracle_fixture(rt, case):
-    """BASELINE C2 (3840x2160, spp 1) at levels 8/9/10 against the committed oracle hashes."""
+BASELINE_CASES = [c for c in DERIVED["cases"] if c["width"] * c["height"] >= 1024 * 768]
+
+
+@pytest.mark.parametrize("case", BASELINE_CASES,
+                         ids=lambda c: "%dx%d_spp%d_L%d" % (c["width"], c["height"], c["spp"], c["level"]))
+def test_baseline_frames_match_oracle_fixture(rt, case):
+    """Every BASELINE configuration, FULL frame, against the committed oracle hash: C1 (1024x768, 4x4, level 8),
+    C2 (3840x2160, 1 spp) at levels 8/9/10, C3 (3840x2160, 4x4, level 9 = C5's frame 0) and C4 (7680x4320, 4x4,
+    level 9) -- plus the ray counts, counted on the device the way the reference's work is counted."""
     gs = rt.Scene(level=case["level"])
-    img = rt.Renderer.render(rt.RenderOptions(case["width"], case["height"], case["spp"]), gs)
+    img, st = rt.Renderer.render(rt.RenderOptions(case["width"], case["height"], case["spp"]), gs, want_stats=True)
     assert hashlib.sha256(img.tobytes()).hexdigest() == case["rgba_sha256"]
+    assert st.variant_used in (rt.VARIANT_TILE, rt.VARIANT_PHASED, rt.VARIANT_PIPE)   # a candidate-list variant ran (no silent LANE fallback)
     p, s = gs.count_rays(case["width"], case["height"], case["spp"])
     assert (p, s) == (case["counters"]["primary_rays"], case["counters"]["shadow_rays"])
+
+
+def test_c5_real_size_orbit_frames_match_oracle_fixture(rt):
+    """BASELINE C5 at real size: orbit frames 7, 41, 88 of the 120-frame sweep (3840x2160, 4x4, level 9) through
+    rt_render_sweep / rt_render_sweep_rgb, against the committed oracle hashes."""
+    cases = DERIVED["c5_cases"]
+    w, h, spp, level = cases[0]["width"], cases[0]["height"], cases[0]["spp"], cases[0]["level"]
+    gs = rt.Scene(level=level)
+    cams = [rt.orbit_camera(c["frame"], c["n_frames"]) for c in cases]
+    got, rgb = {}, {}
+    rt.Renderer.render_sweep(rt.RenderOptions(w, h, spp), gs, len(cams), cameras=cams,
+                             on_frame=lambda i, a: got.__setitem__(i, hashlib.sha256(a.tobytes()).hexdigest()))
+    rt.Renderer.render_sweep(rt.RenderOptions(w, h, spp), gs, len(cams), cameras=cams, rgb=True,
+                             on_frame=lambda i, a: rgb.__setitem__(i, hashlib.sha256(a.tobytes()).hexdigest()))
+    for i, c in enumerate(cases):
+        assert got[i] == c["rgba_sha256"], "orbit frame %d" % c["frame"]
+        assert rgb[i] == c["rgb_sha256"], "orbit frame %d (RGB8)" % c["frame"]
+        assert gs.count_rays(w, h, spp, camera=cams[i]) == (c["counters"]["primary_rays"], c["counters"]["shadow_rays"])
 
 
 def test_render_region_semantics(rt, oracle, gpu_scene8, oracle_scene8):
@@ -392,3 +416,43 @@ def test_phased_occlusion_culling_holds_for_other_eyes(rt, oracle, kw):
         assert tiles.shape[1] == 2 and int(tiles[:, 0][tiles[:, 0] != 0xffffffff].sum()) > 0
     finally:
         rt.set_variant(rt.VARIANT_AUTO)
+
+
+@pytest.mark.parametrize("kw,expect_lane", [
+    (dict(origin=(1000.0, -1.0, 0.0), eye=(1000.0, 0.0, -4.0)), True),     # far from the coordinate origin
+    (dict(origin=(-300.0, 200.0, 150.0), radius=3.0, eye=(-300.0, 203.0, 130.0)), True),
+    (dict(origin=(9.0, -1.0, 3.0), eye=(9.0, 0.0, -1.0)), False),          # translated, still inside the analysed range
+])
+def test_translated_scenes_and_the_variant_that_ran(rt, oracle, kw, expect_lane):
+    """The cull pre-filters carry absolute slacks sized for coordinates below 16 (rt_api.cpp,
+    within_analysed_range): a scene placed far from the origin must take the per-lane walk -- and says so in
+    rt_stats.variant_used -- instead of trusting slacks its coordinate rounding has outgrown; a moderately
+    translated scene stays on the candidate-list path.  Both give the oracle's bytes."""
+    level, w, h, spp = 7, 1280, 720, 1
+    gs, os_ = rt.Scene(level=level, **kw), oracle.Scene(level=level, **kw)
+    ref, _ = os_.render(w, h, spp)
+    for v in (rt.VARIANT_AUTO, rt.VARIANT_PHASED, rt.VARIANT_TILE):
+        rt.set_variant(v)
+        try:
+            img, st = rt.Renderer.render(rt.RenderOptions(w, h, spp), gs, want_stats=True)
+        finally:
+            rt.set_variant(rt.VARIANT_AUTO)
+        assert_same(img, ref, "%s variant %d" % (kw, v))
+        assert (st.variant_used == rt.VARIANT_LANE) == expect_lane, (kw, v, st.variant_used)
+
+
+def test_variant_used_reports_the_fallbacks(rt, gpu_scene8):
+    """rt_stats.variant_used: AUTO resolved, and LANE whenever the arguments leave the candidate-list domain
+    (samples per pixel beyond the templates, an eye inside the root bound)."""
+    def used(scene, w, h, spp, variant=None, camera=None):
+        rt.set_variant(rt.VARIANT_AUTO if variant is None else variant)
+        try:
+            return rt.Renderer.render(rt.RenderOptions(w, h, spp), scene, camera=camera, want_stats=True)[1].variant_used
+        finally:
+            rt.set_variant(rt.VARIANT_AUTO)
+    assert used(gpu_scene8, 2560, 1440, 1) in (rt.VARIANT_PHASED, rt.VARIANT_PIPE)
+    assert used(gpu_scene8, 640, 360, 2) in (rt.VARIANT_TILE, rt.VARIANT_PHASED, rt.VARIANT_PIPE)
+    assert used(gpu_scene8, 64, 64, 9, rt.VARIANT_PHASED) == rt.VARIANT_LANE          # spp beyond the fast path
+    assert used(gpu_scene8, 64, 64, 1, rt.VARIANT_WARP) == rt.VARIANT_WARP
+    inside = rt.Scene(level=6, eye=(0.1, -0.2, -1.6))
+    assert used(inside, 1280, 720, 1, rt.VARIANT_PHASED) == rt.VARIANT_LANE
