@@ -4,26 +4,34 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
 
-A *step* is one pass of the hot path over one frame: ray generation, primary and
-shadow traversal, shading, supersample averaging and RGBA8 quantisation of every
-pixel.  Workload at N=1 (BASELINE.json configs[1], "C2"): the reference's ~20k-sphere
-scene (level 8, 21,845 spheres) at 3840x2160, 1 sample per pixel.  With N>1 every
-rank renders whole frames of that workload (frame-sharded sweep, BASELINE C5's
-partition): no data-path collective, weak scaling.  `--mode bands` instead splits ONE
-frame into interleaved row bands gathered to rank 0 over NCCL (BASELINE C4's
-partition, strong scaling).  `--workload c5` is BASELINE configs[4] itself: the 120-frame
-orbit of the camera about the flake over the level-9 scene at 3840x2160, 4x4 samples,
-step i of rank r rendering frame (i*N + r) mod 120 (c1/c3/c4 select the other configs).
+A *step* is one pass of the hot path over one frame: ray generation, primary and shadow traversal, shading,
+supersample averaging and RGBA8 quantisation of every pixel.
+
+Default line = BASELINE.json configs[4] ("c5"), the largest single-GPU configuration: the 120-frame orbit of
+the camera about the level-9 flake (87,381 spheres) at 3840x2160 with 4x4 samples; step i of rank r renders
+orbit frame (i*N + r) mod 120, so N ranks shard the sweep by frame (no data-path collective, weak scaling).
+Frame 0 is BASELINE configs[2] ("c3").  The same invocation also measures, as sub-records under `also`:
+  c2        configs[1]: the reference's 20k-sphere scene at 3840x2160, 1 spp (the headline 4K render)
+  c4        configs[3] at N=1: one 7680x4320, 4x4, level-9 frame on one GPU
+  c4_bands  configs[3] at N>1: ONE such frame split into interleaved 16-row blocks over the N ranks (strong
+            scaling); kernel-only the blocks land in rank 0's device frame through CUDA-IPC peer stores over
+            NVLink, end to end every rank copies its blocks into one shared pinned host frame over its own
+            PCIe link; a cross-rank barrier closes every frame (frame latency, not throughput)
+`--workload X` measures one workload alone (c1/c2/c3/c3l10/c4/c5), `--mode bands` its row-band split.
 
 metric  = Mrays/s (primary + shadow rays, counted as the reference's work is counted)
-value   = whole-job rays / device time of the K steps (CUDA events on the launch
-          stream, max over ranks), frames written to HBM, nothing leaves the GPU
-e2e     = the same metric through the C ABI with a HOST output buffer
-          (rt_render_frame): kernel-parameter block in, frame out over PCIe, every step
+value   = whole-job rays / device time of the K steps (CUDA events on the launch stream, max over ranks),
+          frames written to HBM, nothing leaves the GPU
+e2e     = the same metric through the C ABI with HOST output buffers: rt_render_sweep_rgb, every frame delivered
+          to pinned host memory (device-to-host copy inside the timed region)
+roofline.frac = EXECUTED FP32 work / measured FFMA peak (hardware view, <= 1); roofline.reference_work is
+          SURVEY 8(d)'s figure (rays x the reference algorithm's flop/ray / time), which exceeds the peak
+          because the candidate lists skip most of the reference's sphere tests.
 """
 import argparse
-import ctypes as C
+import hashlib
 import json
+import mmap
 import os
 import statistics
 import subprocess
@@ -43,11 +51,13 @@ WORKLOADS = {
     "c4": (7680, 4320, 4, 9),
     "c5": (3840, 2160, 4, 9),    # BASELINE configs[4]: 120-frame orbit sweep of C3-sized frames, frame f -> rank f mod N
 }
+DEFAULT_WORKLOAD = "c5"
 ORBIT_FRAMES = 120               # c5: eye and camera basis rotated about the flake's axis by 2 pi f / 120
 # algorithmic flop per ray of REFERENCE work (17 T + 3 P + 19 U + 20 f_p + 30 f_s),
 # from the oracle's counters (tests/golden/oracle_derived.json); used when the fixture lacks the config.
 FLOP_PER_RAY_FALLBACK = 645.0
 METRIC = "Mrays/s (primary+shadow)"
+KERNEL_SOURCES = ("rt_phased.cu", "rt_cull.cuh", "rt_pack.cuh", "rt_device.cuh", "rt_kernels.cu", "rt_tile.cu")
 
 
 def orbit_basis(frame, n_frames=ORBIT_FRAMES, eye=(0.0, 0.0, -4.0)):
@@ -75,31 +85,52 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def flop_per_ray(width, height, spp, level):
+def oracle_case(width, height, spp, level):
     try:
-        cases = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_derived.json")))["cases"]
-        for c in cases:
+        for c in json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_derived.json")))["cases"]:
             if (c["width"], c["height"], c["spp"], c["level"]) == (width, height, spp, level):
-                return c["flop_per_ray"], "oracle counters for this exact config (tests/golden/oracle_derived.json)"
-        for c in cases:  # same resolution, other level: work per ray is flat in depth
-            if (c["width"], c["height"]) == (width, height):
+                return c
+    except Exception:
+        pass
+    return None
+
+
+def flop_per_ray(width, height, spp, level):
+    c = oracle_case(width, height, spp, level)
+    if c:
+        return c["flop_per_ray"], "oracle counters for this exact config (tests/golden/oracle_derived.json)"
+    try:
+        for c in json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_derived.json")))["cases"]:
+            if (c["width"], c["height"]) == (width, height):   # same resolution, other level: flat in depth
                 return c["flop_per_ray"], "oracle counters at %dx%d level %d" % (width, height, c["level"])
     except Exception:
         pass
     return FLOP_PER_RAY_FALLBACK, "SURVEY 8(d) figure for C2"
 
 
+def kernel_source_hash():
+    """sha256 over the kernel sources: a committed ncu capture describes the running kernels only if it was
+    taken from the same sources (profiles/latest_summary.json records the hash it was captured at)."""
+    h = hashlib.sha256()
+    for name in KERNEL_SOURCES:
+        try:
+            h.update(open(os.path.join(ROOT, "rust-tracer_b200", "csrc", name), "rb").read())
+        except OSError:
+            h.update(b"?")
+    return h.hexdigest()[:16]
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons while the benchmark runs (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, index):
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -110,13 +141,17 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def stop(self, t_begin, t_end):
+    def stop(self, windows):
+        """windows: [(t_begin, t_end)] of the timed regions; samples inside them are 'under load'."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
-        rows = [r for (t, r) in self.rows if t_begin - 0.05 <= t <= t_end + 0.15 and len(r) >= 7] or \
-               [r for (_, r) in self.rows if len(r) >= 7]
+        ok = [(t, r) for (t, r) in self.rows if len(r) >= 7]
+        rows = [r for (t, r) in ok if any(a - 0.02 <= t <= b + 0.05 for a, b in windows)]
+        under_load = len(rows)
+        if not rows:
+            rows = [r for (_, r) in ok]
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -130,7 +165,8 @@ class ClockSampler:
         sm = [num(r[0]) for r in rows if num(r[0]) is not None]
         pw = [num(r[2]) for r in rows if num(r[2]) is not None]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": num(rows[0][1]),
-                "power_w_max": max(pw) if pw else None, "samples": len(rows), "reasons": reasons}
+                "power_w_max": max(pw) if pw else None, "samples": len(ok), "samples_under_load": under_load,
+                "reasons": reasons}
 
 
 class stdout_to_stderr:
@@ -151,8 +187,9 @@ class stdout_to_stderr:
 
 
 def pin_to_gpu_cpus(local_rank):
-    """Multi-GPU runs: keep this rank's host threads (and so its pinned frame buffers, first touch) on the
-    CPUs NVML reports as local to its GPU, so that eight ranks copying frames out do not cross sockets."""
+    """Keep this rank's host threads (and so its pinned frame buffers, first touch) on the CPUs NVML reports as
+    local to its GPU, so that frames copied out do not cross sockets (at N=1 too: the end-to-end number is a
+    host-link number)."""
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -171,334 +208,527 @@ def pin_to_gpu_cpus(local_rank):
     return "not pinned"
 
 
-def cpu_leg(width, height, spp, level, min_seconds, row_stride):
-    """The oracle (CPU restatement of the reference algorithm) on every host core."""
+# ---------------------------------------------------------------------------------------------------
+# CPU legs (the oracle: test infrastructure, allowed here as the reported baseline only)
+# ---------------------------------------------------------------------------------------------------
+def cpu_frames(workload, width, height, spp, level, frames, threads):
+    """Whole frames of the workload on `threads` host threads -> (rays, seconds, flop/ray of the last frame)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import _oracle as o   # bench.py's cpu_baseline / reference legs are allowed to run the oracle
-    cores = os.cpu_count() or 1
     s = o.Scene(level=level)
-    rows = (height + row_stride - 1) // row_stride
     rays = secs = 0.0
-    reps = 0
     ctr = None
-    while secs < min_seconds or reps == 0:
+    for f in frames:
+        cam = o.make_camera(*orbit_basis(f % ORBIT_FRAMES)) if workload == "c5" else None
         t0 = time.perf_counter()
-        _, ctr = s.render_rows(width, height, spp, 0, row_stride, rows, threads=cores)
+        _, ctr = s.render_rows(width, height, spp, 0, 1, height, threads=threads, camera=cam)
         secs += time.perf_counter() - t0
         rays += ctr.primary_rays + ctr.shadow_rays
-        reps += 1
-    sample = "rows 0,%d,%d,.. (%d of %d rows) of the %dx%d spp %d level %d frame, %d repeat(s), %.1f s" % (
-        row_stride, 2 * row_stride, rows, height, width, height, spp, level, reps, secs)
-    return {"value": rays / secs / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample,
-            "flop_per_ray": ctr.flop_per_ray()}, rays / reps, secs / reps
+    return rays, secs, (ctr.flop_per_ray() if ctr else None)
 
 
-def run_reference(args, width, height, spp, level):
-    """--impl reference: the reference's CPU algorithm (oracle port; the Rust binary cannot be built
-    here: no cargo/rustc) on all host threads, same metric and config.  Rank 0 only."""
+def cpu_leg(workload, width, height, spp, level, budget_s=12.0):
+    """cpu_baseline of the native line: whole frames of the same workload on every host core, bounded to about
+    `budget_s` seconds (at least one frame)."""
+    cores = os.cpu_count() or 1
+    rays = secs = 0.0
+    n, fpr = 0, None
+    while n == 0 or (secs < budget_s and secs / n * (n + 1) < 2.5 * budget_s):
+        r, s, fpr = cpu_frames(workload, width, height, spp, level, [n], cores)
+        rays, secs, n = rays + r, secs + s, n + 1
+    what = "orbit frame(s) 0..%d" % (n - 1) if workload == "c5" else "%d repeat(s) of the frame" % n
+    return {"value": rays / secs / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+            "sample": "%s, whole %dx%d spp %d level %d frames, %.1f s" % (what, width, height, spp, level, secs),
+            "flop_per_ray": fpr}
+
+
+def run_reference(args, workload):
+    """--impl reference: the reference's CPU algorithm (oracle port; the Rust crate cannot be built here: no
+    cargo/rustc) on all host threads -- same metric, same config, whole frames, the same warm-up and step counts
+    as the native arm.  Rank 0 only.  A run that would pass ~200 s stops early and says so in `steps`."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import _oracle as o
+    width, height, spp, level = WORKLOADS[workload]
     cores = os.cpu_count() or 1
-    s = o.Scene(level=level)
-    stride = 4   # each step renders every 4th row: an unbiased quarter of the frame
-    rows = (height + stride - 1) // stride
-    for _ in range(min(args.warmup, 1)):
-        s.render_rows(width, height, spp, 0, stride, rows, threads=cores)
-    rays = 0
-    t0 = time.perf_counter()
-    budget_steps = args.steps
-    done = 0
-    for i in range(budget_steps):
-        cam = None
-        if args.workload == "c5":   # orbit sweep: step i is frame i of the orbit (same cameras as the native arm)
-            cam = o.make_camera(*orbit_basis(i % ORBIT_FRAMES))
-        _, ctr = s.render_rows(width, height, spp, 0, stride, rows, threads=cores, camera=cam)
-        rays += ctr.primary_rays + ctr.shadow_rays
-        done += 1
-        if time.perf_counter() - t0 > 150.0:   # keep the whole run within a few minutes
+    t_all = time.perf_counter()
+    wdone = 0
+    for i in range(args.warmup):
+        cpu_frames(workload, width, height, spp, level, [i], cores)
+        wdone += 1
+        if time.perf_counter() - t_all > 60.0:
             break
-    secs = time.perf_counter() - t0
+    rays = secs = 0.0
+    done = 0
+    for i in range(args.steps):
+        r, s, _ = cpu_frames(workload, width, height, spp, level, [i], cores)
+        rays, secs, done = rays + r, secs + s, done + 1
+        if time.perf_counter() - t_all > 200.0:   # keep the whole run within a few minutes on any host
+            break
     v = rays / secs / 1e6
-    sample = "each step = rows 0,4,8,.. (%d of %d) of the frame on %d host threads; %d steps timed" % (rows, height, cores, done)
+    sample = "each step = one whole %dx%d spp %d level %d frame%s on %d host threads; %d of %d steps timed" % (
+        width, height, spp, level, " (orbit frame i)" if workload == "c5" else "", cores, done, args.steps)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": done,
-        "warmup": min(args.warmup, 1), "ms_per_step": secs / done * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": wdone, "ms_per_step": secs / done * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.workload, level, width, height, spp)},
+        "config": {"workload": workload_name(workload, level, width, height, spp)},
         "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--mode", default="frames", choices=["frames", "bands"],
-                    help="N>1: 'frames' = each rank renders whole frames (weak); 'bands' = one frame split "
-                         "into interleaved rows gathered to rank 0 over NCCL (strong)")
-    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
-                    help="bands mode: 'peer' = every rank's kernel stores its rows straight into rank 0's frame "
-                         "through CUDA-IPC peer memory over NVLink; 'nccl' = dist.gather of the bands + de-interleave")
-    ap.add_argument("--variant", type=int, default=0)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-l2-flush", action="store_true")
-    args = ap.parse_args()
-    width, height, spp, level = WORKLOADS[args.workload]
-    if args.warmup < 3 and args.impl == "native":
-        args.warmup = 3   # timing rule: at least 3 warm-up steps
+# ---------------------------------------------------------------------------------------------------
+# native arm
+# ---------------------------------------------------------------------------------------------------
+class Job:
+    """Process-wide state of the native arm: rank / world, device, library, clocks."""
 
-    if args.impl == "reference":
-        run_reference(args, width, height, spp, level)
-        return
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        import rtrace_b200 as rt   # raises ImportError if the CUDA library is not built: no fallback
+        self.torch, self.dist, self.rt, self.args = torch, dist, rt, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.cpu_note = None if os.environ.get("RTRACE_NO_PIN") else pin_to_gpu_cpus(self.local_rank)
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; this benchmark has no CPU fallback (use --impl reference)")
+        torch.cuda.set_device(self.local_rank)
+        rt.set_device(self.local_rank)
+        if self.world > 1:
+            with stdout_to_stderr():   # communicator creation and the first collective: NCCL's banner
+                dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+                dist.barrier()
+        rt.set_variant(args.variant)
+        self.stream = torch.cuda.current_stream()
+        self.flush = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        self.windows = []
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        self.sampler = ClockSampler(vis.split(",")[self.local_rank] if vis else torch.cuda.current_device()) \
+            if self.rank == 0 else None
+        self.peaks = {}
+        try:
+            self.peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        self._fp32 = None
 
-    import torch
-    import torch.distributed as dist
-    import rtrace_b200 as rt   # raises ImportError if the CUDA library is not built: no fallback
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    cpu_note = pin_to_gpu_cpus(local_rank) if world > 1 and not os.environ.get("RTRACE_NO_PIN") else None
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; this benchmark has no CPU fallback (use --impl reference)")
-    torch.cuda.set_device(local_rank)
-    rt.set_device(local_rank)
-    if world > 1:
-        with stdout_to_stderr():   # communicator creation and the first collective: NCCL's banner
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-            dist.barrier()
-    rt.set_variant(args.variant)
+    def reduce(self, values):
+        """(max over ranks, sum over ranks) of a list of floats."""
+        t = self.torch.tensor(values, dtype=self.torch.float64, device="cuda")
+        if self.world == 1:
+            return t.tolist(), t.tolist()
+        tmax, tsum = t.clone(), t.clone()
+        self.dist.all_reduce(tmax, op=self.dist.ReduceOp.MAX)
+        self.dist.all_reduce(tsum, op=self.dist.ReduceOp.SUM)
+        return tmax.tolist(), tsum.tolist()
 
+    def fp32_peak(self):
+        if self._fp32 is None:
+            try:
+                tf, mhz = self.rt.measure_fp32_peak(self.local_rank)
+                self._fp32 = (tf, "measured live: FFMA chains on all SMs (rt_measure_fp32_peak), effective %.0f MHz; "
+                                  "MEASURED_PEAKS.json has no FP32 entry" % mhz)
+            except Exception as e:   # pragma: no cover
+                self._fp32 = (148 * 128 * 2 * 1.965e9 / 1e12, "nominal 148 SM x 128 lanes x 2 x 1965 MHz (%s)" % e)
+        return self._fp32
+
+    def timed(self, steps, step_fn, pre_fn=None):
+        """K steps between CUDA events on the launch stream, L2 flushed before each (outside the events).
+        Returns (device ms summed over the steps, wall ms)."""
+        torch = self.torch
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        t_begin = time.time()
+        w0 = time.perf_counter()
+        for i, (a, b) in enumerate(ev):
+            if self.flush is not None:
+                self.flush.zero_()          # evict L2 (126 MB) between timed steps; outside the event pair
+            if pre_fn:
+                pre_fn(i)
+            a.record(self.stream)
+            step_fn(i)
+            b.record(self.stream)
+        self.barrier()
+        wall_ms = (time.perf_counter() - w0) * 1e3
+        self.windows.append((t_begin, time.time()))
+        return sum(a.elapsed_time(b) for a, b in ev), wall_ms
+
+    def pcie(self, nbytes):
+        """Copy-only ceiling of the end-to-end numbers: every rank copies `nbytes` frames device -> pinned host at
+        the same time (barrier first); returns this job's aggregate GB/s and rank 0's own rate."""
+        self.barrier()
+        g = self.rt.microbench_d2h(nbytes, 24)
+        (gmax,), (gsum,) = self.reduce([g])
+        return gsum, g
+
+
+def roofline_block(job, workload, width, height, spp, level, rays_per_launch, ms_per_step, fb_bytes):
+    """Hardware view first: executed FP32 flops per frame (from the committed ncu capture of THIS workload, used
+    only if it was taken from the same kernel sources) / live time / live FFMA peak.  SURVEY 8(d)'s reference-work
+    figure travels beside it under its own name."""
+    peak_tf, peak_src = job.fp32_peak()
+    fpr, fpr_src = flop_per_ray(width, height, spp, level)
+    ref_tf = rays_per_launch * fpr / (ms_per_step * 1e-3) / 1e12
+    cap, note = None, "no ncu capture of this workload in profiles/latest_summary.json"
+    try:
+        summ = json.load(open(os.path.join(ROOT, "profiles", "latest_summary.json")))
+        c = summ.get("workloads", {}).get(workload if workload != "c5" else "c3")
+        if c and summ.get("kernel_source_hash") == kernel_source_hash():
+            cap, note = c, None
+        elif c:
+            note = "the committed capture (%s) was taken from other kernel sources: not used" % summ.get("kernel_source_hash")
+    except Exception:
+        pass
+    hbm_peak = job.peaks.get("hbm_gbs", 6650.0)
+    out = {"bound": "fp32", "unit": "TFLOP/s", "peak": peak_tf, "peak_source": peak_src}
+    if cap:
+        ex_tf = cap["fp32_flop_per_frame"] / (ms_per_step * 1e-3) / 1e12
+        out.update({
+            "achieved": ex_tf, "frac": ex_tf / peak_tf, "traffic": cap.get("dram_bytes_per_frame"),
+            "executed": {k: cap[k] for k in ("fp32_flop_per_frame", "warp_instructions_per_frame", "fma_pipe_active_pct",
+                                             "issue_active_pct", "dominant_kernel", "dominant_kernel_share", "source")
+                         if k in cap},
+            "note": "achieved = FP32 flops the kernels EXECUTE per frame (ncu thread-level FADD+FMUL+2*FFMA counts of this "
+                    "workload, committed capture of the same sources; the work is deterministic) / live event time; "
+                    "traffic = DRAM bytes per frame of the same capture (cold L2: ncu flushes it between replays)"})
+    else:
+        out.update({"achieved": None, "frac": None, "traffic": None, "executed": None, "note": note})
+    out["reference_work"] = {
+        "achieved": ref_tf, "frac_of_peak": ref_tf / peak_tf, "flop_per_ray": fpr,
+        "note": "SURVEY 8(d): rays/launch x algorithmic flop/ray of the REFERENCE walk (%s) / event time. Not a hardware "
+                "roofline: the candidate lists replace ~34 sphere tests per ray by 1-2 exact tests, so this exceeds the "
+                "FP32 peak on supersampled frames" % fpr_src}
+    hb = fb_bytes / (ms_per_step * 1e-3) / 1e9
+    out["hbm"] = {"achieved": hb, "peak": hbm_peak, "unit": "GB/s", "frac": hb / hbm_peak,
+                  "note": "algorithmic HBM bytes = framebuffer written once (4 B/pixel); peak = MEASURED_PEAKS.json hbm_gbs"
+                          if job.peaks else "peak = fallback 6.65 TB/s"}
+    return out
+
+
+def measure_frames(job, workload, steps, warmup, cpu_baseline=False):
+    """Whole frames per rank (frame-sharded; for c5 the orbit): kernel-only `value` and the end-to-end sweep."""
+    rt, torch = job.rt, job.torch
+    rank, world = job.rank, job.world
+    width, height, spp, level = WORKLOADS[workload]
+    sweep = workload == "c5"
     scene = rt.Scene(level=level)
     opts = rt.RenderOptions(width, height, spp)
-    stream = torch.cuda.current_stream()
-    bands = args.mode == "bands" and world > 1
-    sweep = args.workload == "c5"
-    if sweep and bands:
-        raise SystemExit("bench.py: c5 is the frame-sharded orbit sweep; use --mode frames")
     cams = [rt.make_camera(*orbit_basis(f)) for f in range(ORBIT_FRAMES)] if sweep else None
 
     def frame_of(i):   # c5: step i of this rank renders orbit frame (i * world + rank) mod 120
         return (i * world + rank) % ORBIT_FRAMES
-    from rtrace_b200 import partition
-    if bands:
-        row_start, row_stride, my_rows = partition.band_spec(height, rank, world)
-        max_rows = partition.band_capacity(height, world)
-    else:
-        my_rows, max_rows, row_start, row_stride = height, height, 0, 1
-    fb = torch.zeros((max_rows + 16, width, 4), dtype=torch.uint8, device="cuda")   # + one row block (blocked partition)
-    gathered = [torch.zeros_like(fb[:max_rows]) for _ in range(world)] if (bands and rank == 0) else None
-    frame_box = [None]
-    peer = bands and args.gather == "peer"
-    peer_ptr, peer_pitch = None, 0
-    if peer:
-        # rank 0 owns the frame; the others map it through a CUDA IPC handle and write their rows into it
-        handle = torch.zeros(64, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            frame_base = rt.device_alloc(height * width * 4)
-            handle.copy_(torch.frombuffer(bytearray(rt.ipc_export(frame_base)), dtype=torch.uint8))
-        dist.broadcast(handle, src=0)
-        if rank != 0:
-            frame_base = rt.ipc_open(bytes(handle.cpu().numpy().tobytes()))
-        # blocks of 16 consecutive rows per rank (whole cull tiles stay contiguous in the image)
-        row_start, row_stride, row_block, my_rows = partition.block_band_spec(height, rank, world, 16)
-
-    # kernels launched per step (the PHASED variant is four launches per frame)
-    _, st0 = rt.Renderer.render_rows(opts, scene, row_start=0, row_stride=1, row_count=min(my_rows, height),
-                                     out_ptr=fb.data_ptr(), stream=stream.cuda_stream, want_stats=True)
-    launches_per_step = int(st0.kernel_launches)
-    # rays of this rank's share of a step, counted on the device the way the reference's work is counted
-    if peer:   # blocked partition: count whole-frame rays once; each rank gets its share by pixel count
-        primary_all, shadow_all = scene.count_rays(width, height, spp)
-        primary = width * my_rows * spp * spp
-        shadow = int(round(shadow_all * my_rows / height))
-    else:
-        primary, shadow = scene.count_rays(width, height, spp, row_start, row_stride, my_rows)
-    rays_rank = primary + shadow
-    e2e_steps = max(5, min(args.steps, 100))
-    e2e_rays_rank = rays_rank
-    if sweep:   # every orbit frame casts its own number of shadow rays: count each frame this rank renders
-        table = {}
-        for f in sorted({frame_of(i) for i in range(max(args.steps, e2e_steps))}):
-            table[f] = scene.count_rays(width, height, spp, camera=cams[f])
-        primary = sum(table[frame_of(i)][0] for i in range(args.steps)) / args.steps
-        shadow = sum(table[frame_of(i)][1] for i in range(args.steps)) / args.steps
-        rays_rank = primary + shadow                      # mean per timed step
+    fb = torch.zeros((height, width, 4), dtype=torch.uint8, device="cuda")
+    _, st0 = rt.Renderer.render_rows(opts, scene, out_ptr=fb.data_ptr(), stream=job.stream.cuda_stream, want_stats=True)
+    launches_per_step, variant_used = int(st0.kernel_launches), int(st0.variant_used)
+    e2e_steps = max(5, min(steps, 100))
+    # rays of this rank's steps, counted on the device the way the reference's work is counted
+    if sweep:
+        table = {f: scene.count_rays(width, height, spp, camera=cams[f])
+                 for f in sorted({frame_of(i) for i in range(max(steps, e2e_steps))})}
+        primary = sum(table[frame_of(i)][0] for i in range(steps)) / steps
+        shadow = sum(table[frame_of(i)][1] for i in range(steps)) / steps
         e2e_rays_rank = sum(sum(table[frame_of(i)]) for i in range(e2e_steps)) / e2e_steps
-    flush = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    else:
+        primary, shadow = scene.count_rays(width, height, spp)
+        e2e_rays_rank = primary + shadow
+    rays_rank = primary + shadow
 
-    def step(i=0):
-        if sweep:
-            rt.Renderer.render_rows(opts, scene, camera=cams[frame_of(i)], out_ptr=fb.data_ptr(),
-                                    stream=stream.cuda_stream)
-            return
-        if peer:   # the traversal kernels' framebuffer stores ARE the gather (NVLink peer writes)
-            rt.Renderer.render_row_blocks(opts, scene, row_start, row_stride, row_block, my_rows, frame_base,
-                                          pitch=width * 4, absolute_rows=True, stream=stream.cuda_stream)
-            return
-        rt.Renderer.render_rows(opts, scene, row_start=row_start, row_stride=row_stride, row_count=my_rows,
-                                out_ptr=fb.data_ptr(), stream=stream.cuda_stream)
-        if bands:
-            dist.gather(fb[:max_rows], gathered, dst=0)
-            if rank == 0:   # de-interleave: row r*world + g  <-  band g row r
-                frame_box[0] = partition.deinterleave(gathered, height)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else
-                           os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]) if rank == 0 else None
-    for i in range(args.warmup):
+    def step(i):
+        rt.Renderer.render_rows(opts, scene, camera=cams[frame_of(i)] if sweep else None, out_ptr=fb.data_ptr(),
+                                stream=job.stream.cuda_stream)
+    for i in range(warmup):
         step(i)
-    barrier()
+    job.barrier()
+    dev_ms, wall_ms = job.timed(steps, step)
 
-    # ---- value: K steps, device time from CUDA events on the launch stream --------------------
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    t_begin = time.time()
-    w0 = time.perf_counter()
-    for i, (a, b) in enumerate(ev):
-        if flush is not None:
-            flush.zero_()          # evict L2 (126 MB) between timed steps; outside the event pair
-        a.record(stream)
-        step(i)
-        b.record(stream)
-    barrier()
-    wall_ms = (time.perf_counter() - w0) * 1e3
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-
-    peer_ok = None
-    if peer:
-        barrier()
-        if rank == 0:   # the gathered frame must equal a frame rendered by rank 0 alone
-            import numpy as _np
-            whole = torch.zeros((height, width, 4), dtype=torch.uint8, device="cuda")
-            rt.Renderer.render_rows(opts, scene, out_ptr=whole.data_ptr(), stream=stream.cuda_stream)
-            torch.cuda.synchronize()
-            got = rt.PinnedBuffer(height * width * 4)
-            rt.memcpy(got.ptr, frame_base, got.nbytes)
-            peer_ok = bool(_np.array_equal(got.array.reshape(height, width, 4), whole.cpu().numpy()))
-        barrier()
-
-    # ---- e2e: the C-ABI call a user makes, every frame delivered to HOST memory ----------------
-    # frames mode: rt_render_sweep (what `rtrace --frames` calls): the device-to-host copy of frame f
-    # overlaps the render of frame f+1; the callback sees every frame in pinned host memory.
-    # bands mode: rt_render_rows into a pinned host buffer, synchronously.
+    # ---- e2e: the C-ABI call a user makes, every frame delivered to HOST memory ----
     seen = []
 
     def on_frame(f, arr):
         seen.append(int(arr[0, 0, 0]))   # touch the host copy of every frame
 
-    e_start, e_stride, e_rows = partition.band_spec(height, rank, world) if bands else (0, 1, height)
-    pinned = rt.PinnedBuffer(max(e_rows, 1) * width * 4) if bands else None
-
     def e2e_run(n):
-        if bands:
-            for _ in range(n):
-                rt.Renderer.render_rows(opts, scene, row_start=e_start, row_stride=e_stride, row_count=e_rows,
-                                        out_ptr=pinned.ptr)
-        else:
-            rt.Renderer.render_sweep(opts, scene, n, on_frame=on_frame, rgb=True,
-                                     cameras=[cams[frame_of(i)] for i in range(n)] if sweep else None)
-
+        rt.Renderer.render_sweep(opts, scene, n, on_frame=on_frame, rgb=True,
+                                 cameras=[cams[frame_of(i)] for i in range(n)] if sweep else None)
     e2e_run(3)
-    barrier()
+    job.barrier()
+    t_begin = time.time()
     e0 = time.perf_counter()
     e2e_run(e2e_steps)
-    barrier()
+    job.barrier()
     e2e_ms = (time.perf_counter() - e0) * 1e3
-    t_end = time.time()
-    clocks = sampler.stop(t_begin, t_end) if sampler else None
+    job.windows.append((t_begin, time.time()))
+    d2h = width * height * 3
+    pcie_sum, pcie_own = job.pcie(d2h)
 
-    # ---- max over ranks ------------------------------------------------------------------------
-    t = torch.tensor([dev_ms, e2e_ms, float(rays_rank), float(e2e_rays_rank)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        dev_ms, e2e_ms, rays_job, e2e_rays_job = tmax[0].item(), tmax[1].item(), tsum[2].item(), tsum[3].item()
-    else:
-        rays_job, e2e_rays_job = float(rays_rank), float(e2e_rays_rank)
+    (dev_ms, e2e_ms, _, _), (_, _, rays_job, e2e_rays_job) = job.reduce([dev_ms, e2e_ms, float(rays_rank), float(e2e_rays_rank)])
+    if rank != 0:
+        return None
+    ms_per_step = dev_ms / steps
+    e2e_step = e2e_ms / e2e_steps
+    rec = {
+        "metric": METRIC, "value": rays_job / (ms_per_step * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": workload_name(workload, level, width, height, spp),
+            "partition": "one whole frame per rank per step (frame-sharded sweep), no collective",
+            "l2": "not flushed" if job.flush is None else "flushed between steps (256 MiB memset, outside the timed events)",
+            "rays_per_frame": {"primary": primary, "shadow": shadow},
+            "mpixels_per_s": width * height * world / (ms_per_step * 1e-3) / 1e6,
+            "variant": job.args.variant, "variant_used": variant_used,
+            "wall_ms_per_step_incl_flush": wall_ms / steps, "host_cpus": job.cpu_note,
+        },
+        "roofline": roofline_block(job, workload, width, height, spp, level, rays_job / world, ms_per_step, width * height * 4),
+        "e2e": {"value": e2e_rays_job / (e2e_step * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 512,
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_step,
+                "pcie": {"achieved_gbs": d2h * world / (e2e_step * 1e-3) / 1e9, "ceiling_gbs": pcie_sum,
+                         "frac": d2h * world / (e2e_step * 1e-3) / 1e9 / pcie_sum, "rank0_alone_gbs": pcie_own,
+                         "note": "achieved = frame bytes leaving all GPUs / e2e time; ceiling = copy-only rate with every "
+                                 "rank copying at once (rt_microbench_d2h, pinned host memory, no kernels)"},
+                "note": "rt_render_sweep_rgb (what `rtrace --frames` calls): per frame the kernel-parameter blocks (camera, "
+                        "options) go in and the RGB8 frame -- the body of the reference's P6 file, its sink drops alpha "
+                        "(render.rs:389-397) -- comes out to pinned host memory; two frames render at a time while an "
+                        "earlier one is copied out"},
+        "gpu_launches": steps * world * launches_per_step,
+    }
+    if cpu_baseline:
+        rec["cpu_baseline"] = cpu_leg(workload, width, height, spp, level)
+    return rec
 
+
+class SharedHostFrame:
+    """One frame in a POSIX shared-memory segment, page-locked in every rank: each GPU copies its row blocks into
+    it over its own PCIe link, rank 0 (the sink) reads the whole frame."""
+
+    def __init__(self, job, nbytes, tag):
+        self.job, self.nbytes = job, nbytes
+        self.path = "/dev/shm/rtrace_bench_%s_%s" % (os.environ.get("MASTER_PORT", "0"), tag)
+        if job.rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(nbytes)
+        job.barrier()
+        self.f = open(self.path, "r+b")
+        self.mm = mmap.mmap(self.f.fileno(), nbytes)
+        import ctypes
+        import numpy as np
+        self.array = np.frombuffer(self.mm, dtype=np.uint8)
+        self.ptr = ctypes.addressof(ctypes.c_char.from_buffer(self.mm))
+        job.rt.host_register(self.ptr, nbytes)
+
+    def close(self):
+        try:
+            self.job.rt.host_unregister(self.ptr)
+        except Exception:
+            pass
+        self.job.barrier()
+        self.array = None
+        if self.job.rank == 0:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+
+
+def measure_bands(job, workload, steps, warmup, gather="peer"):
+    """ONE frame per step split over the ranks in interleaved 16-row blocks (strong scaling).  Kernel-only: the
+    kernels store straight into rank 0's device frame through CUDA-IPC peer memory (NVLink), a cross-rank barrier
+    closes every frame.  End to end: every rank renders its blocks and copies them into one shared pinned HOST
+    frame over its own PCIe link; barrier; the frame is complete in rank 0's address space."""
+    rt, torch, dist = job.rt, job.torch, job.dist
+    rank, world = job.rank, job.world
+    from rtrace_b200 import partition
+    width, height, spp, level = WORKLOADS[workload]
+    scene = rt.Scene(level=level)
+    opts = rt.RenderOptions(width, height, spp)
+    block = 16
+    row_start, row_stride, row_block, my_rows = partition.block_band_spec(height, rank, world, block)
+    row_bytes = width * 4
+    # rank 0 owns the device frame; the others map it through a CUDA IPC handle
+    handle = torch.zeros(64, dtype=torch.uint8, device="cuda")
     if rank == 0:
-        ms_per_step = dev_ms / args.steps
-        value = rays_job / (ms_per_step * 1e-3) / 1e6
-        e2e_value = e2e_rays_job / (e2e_ms / e2e_steps * 1e-3) / 1e6
-        fpr, fpr_src = flop_per_ray(width, height, spp, level)
-        try:
-            peak_tf, eff_mhz = rt.measure_fp32_peak(local_rank)
-            peak_src = "measured live: FFMA chains on all SMs (rt_measure_fp32_peak), effective %.0f MHz" % eff_mhz
-        except Exception as e:   # pragma: no cover
-            peak_tf, peak_src = 148 * 128 * 2 * 1.965e9 / 1e12, "nominal 148 SM x 128 lanes x 2 x 1965 MHz (%s)" % e
-        # per-launch figures for the dominant (only) kernel: one launch per step per rank
-        rays_launch = rays_job / world if not bands else rays_job / world
-        achieved_tf = rays_launch * fpr / (ms_per_step * 1e-3) / 1e12
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        fb_bytes = my_rows * width * 4
-        traffic, ncu_facts = None, None
-        try:
-            summ = json.load(open(os.path.join(ROOT, "profiles", "latest_summary.json"))).get(args.workload, {})
-            traffic = summ.get("dram_bytes_per_launch")
-            ncu_facts = {k: summ[k] for k in ("dominant_kernel", "fma_pipe_cycles_active_pct", "issue_active_pct",
-                                              "warp_instructions_per_frame", "source") if k in summ} or None
-        except Exception:
-            pass
-        out = {
-            "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong" if bands else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": workload_name(args.workload, level, width, height, spp),
-                "partition": (("interleaved row bands; kernels store into rank 0's frame through IPC peer memory (NVLink)"
-                               " in blocks of 16 rows" if peer else "interleaved row bands + NCCL gather to rank 0") if bands else
-                              "one whole frame per rank per step (frame-sharded sweep), no collective"),
-                "l2": "not flushed" if flush is None else "flushed between steps (256 MiB memset, outside the timed events)",
-                "rays_per_frame": {"primary": primary * (world if bands else 1), "shadow": None if bands else shadow},
-                "mpixels_per_s": width * height * (1 if bands else world) / (ms_per_step * 1e-3) / 1e6,
-                "variant": args.variant, "wall_ms_per_step_incl_flush": wall_ms / args.steps, "host_cpus": cpu_note,
-            },
-            "roofline": {
-                "bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": traffic,
-                "ncu": ncu_facts,   # what the hardware actually did (committed ncu capture), next to the reference-work figure
-                "note": "path is FP32-issue bound, not HBM/tensor (SURVEY 8d): achieved = rays/launch x %.1f "
-                        "algorithmic flop/ray of REFERENCE work (%s) / event time; peak = %s" % (fpr, fpr_src, peak_src),
-                "hbm": {"achieved": fb_bytes / (ms_per_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": fb_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
-                        "note": "algorithmic HBM bytes = framebuffer written once (4 B/pixel); peak = MEASURED_PEAKS.json hbm_gbs" if peaks else "peak = fallback 6.65 TB/s"},
-            },
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 512,
-                    "d2h_bytes_per_step": fb_bytes if bands else fb_bytes // 4 * 3, "steps": e2e_steps,
-                    "ms_per_step": e2e_ms / e2e_steps,
-                    "note": ("rt_render_rows -> pinned host buffer, synchronous" if bands else
-                             "rt_render_sweep_rgb (what `rtrace --frames` calls): per frame the kernel-parameter blocks "
-                             "(camera, options) go in and the RGB8 frame -- the body of the reference's P6 file, its sink "
-                             "drops alpha (render.rs:389-397) -- comes out to pinned host memory; copy of frame f "
-                             "overlaps the render of frame f+1")},
-            "gpu_launches": args.steps * world * launches_per_step,
-            "gathered_frame_verified": peer_ok,
-            "clocks": clocks,
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            cb, _, _ = cpu_leg(width, height, spp, level, 10.0, 1)
-            out["cpu_baseline"] = cb
+        frame_base = rt.device_alloc(height * row_bytes)
+        handle.copy_(torch.frombuffer(bytearray(rt.ipc_export(frame_base)), dtype=torch.uint8))
+    if world > 1:
+        dist.broadcast(handle, src=0)
+    if rank != 0:
+        frame_base = rt.ipc_open(bytes(handle.cpu().numpy().tobytes()))
+    own = torch.zeros((height, width, 4), dtype=torch.uint8, device="cuda")   # e2e: this rank's blocks at their image rows
+    nccl_band = torch.zeros((partition.band_capacity(height, world), width, 4), dtype=torch.uint8, device="cuda")
+    gathered = [torch.zeros_like(nccl_band) for _ in range(world)] if (gather == "nccl" and rank == 0) else None
+
+    st0 = rt.Renderer.render_row_blocks(opts, scene, row_start, row_stride, row_block, my_rows, own.data_ptr(),
+                                        pitch=row_bytes, absolute_rows=True, stream=job.stream.cuda_stream, want_stats=True)
+    launches_per_step = int(st0.kernel_launches)
+    primary_all, shadow_all = scene.count_rays(width, height, spp)
+    rays_frame = primary_all + shadow_all
+    sync_flag = torch.zeros(1, device="cuda")
+
+    def frame_sync():   # cross-rank: every rank's kernels of this frame have finished (NCCL all-reduce on the stream)
+        if world > 1:
+            dist.all_reduce(sync_flag)
+
+    def step(i, synced=True):
+        if gather == "nccl":
+            s0, s1, n = partition.band_spec(height, rank, world)
+            rt.Renderer.render_rows(opts, scene, row_start=s0, row_stride=s1, row_count=n, out_ptr=nccl_band.data_ptr(),
+                                    stream=job.stream.cuda_stream)
+            dist.gather(nccl_band, gathered, dst=0)
+            return
+        rt.Renderer.render_row_blocks(opts, scene, row_start, row_stride, row_block, my_rows, frame_base, pitch=row_bytes,
+                                      absolute_rows=True, stream=job.stream.cuda_stream)
+        if synced:
+            frame_sync()
+    for i in range(warmup):
+        step(i)
+    job.barrier()
+    dev_ms, wall_ms = job.timed(steps, step)
+    thr_ms, _ = job.timed(steps, lambda i: step(i, synced=False)) if gather == "peer" else (dev_ms, 0)
+
+    # the gathered device frame against the ORACLE's hash of this configuration
+    verified = None
+    job.barrier()
+    case = oracle_case(width, height, spp, level)
+    if rank == 0 and gather == "peer":
+        got = rt.PinnedBuffer(height * row_bytes)
+        rt.memcpy(got.ptr, frame_base, got.nbytes)
+        verified = (hashlib.sha256(got.array.tobytes()).hexdigest() == case["rgba_sha256"]) if case else None
+        got.close()
+    job.barrier()
+
+    # ---- e2e: one shared pinned host frame, every rank copies its own blocks into it ----
+    host = SharedHostFrame(job, height * row_bytes, workload)
+    whole, tail = my_rows // block, my_rows % block
+    blk, pitch, off = block * row_bytes, row_stride * row_bytes, row_start * row_bytes
+
+    def e2e_step(i):
+        rt.Renderer.render_row_blocks(opts, scene, row_start, row_stride, row_block, my_rows, own.data_ptr(),
+                                      pitch=row_bytes, absolute_rows=True, stream=job.stream.cuda_stream)
+        if whole:
+            rt.memcpy2d_async(host.ptr + off, pitch, own.data_ptr() + off, pitch, blk, whole, job.stream.cuda_stream)
+        if tail:
+            rt.memcpy2d_async(host.ptr + off + whole * pitch, pitch, own.data_ptr() + off + whole * pitch, pitch,
+                              tail * row_bytes, 1, job.stream.cuda_stream)
+        job.barrier()          # the frame is complete in host memory on every rank's view
+        if rank == 0:
+            _ = int(host.array[0]) + int(host.array[-1])   # the sink touches the frame
+        if world > 1:
+            dist.barrier()     # nobody overwrites the frame before the sink is done with it
+    for i in range(3):
+        e2e_step(i)
+    e2e_steps = max(5, min(steps, 50))
+    job.barrier()
+    t_begin = time.time()
+    e0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    e2e_ms = (time.perf_counter() - e0) * 1e3
+    job.windows.append((t_begin, time.time()))
+    e2e_verified = None
+    if rank == 0 and case:
+        e2e_verified = hashlib.sha256(host.array.tobytes()).hexdigest() == case["rgba_sha256"]
+    my_bytes = my_rows * row_bytes
+    pcie_sum, pcie_own = job.pcie(max(my_bytes, 1 << 20))
+    host.close()
+    if rank == 0:
+        rt.device_free(frame_base)
+    else:
+        rt.ipc_close(frame_base)
+
+    (dev_ms, thr_ms, e2e_ms), _ = job.reduce([dev_ms, thr_ms, e2e_ms])
+    if rank != 0:
+        return None
+    ms_per_step, e2e_step_ms = dev_ms / steps, e2e_ms / e2e_steps
+    return {
+        "metric": METRIC, "value": rays_frame / (ms_per_step * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": workload_name(workload, level, width, height, spp),
+            "partition": ("ONE frame per step in interleaved blocks of 16 rows; kernels store into rank 0's frame through IPC "
+                          "peer memory (NVLink); an all-reduce on the stream closes every frame (ms_per_step is a frame latency)"
+                          if gather == "peer" else "interleaved row bands + NCCL gather to rank 0"),
+            "l2": "not flushed" if job.flush is None else "flushed between steps (256 MiB memset, outside the timed events)",
+            "rays_per_frame": {"primary": primary_all, "shadow": shadow_all},
+            "mpixels_per_s": width * height / (ms_per_step * 1e-3) / 1e6,
+            "unsynchronised_throughput_mrays_s": rays_frame / (thr_ms / steps * 1e-3) / 1e6,
+            "wall_ms_per_step_incl_flush": wall_ms / steps,
+        },
+        "e2e": {"value": rays_frame / (e2e_step_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 512,
+                "d2h_bytes_per_step": height * row_bytes, "steps": e2e_steps, "ms_per_step": e2e_step_ms,
+                "gathered_frame_verified": e2e_verified,
+                "pcie": {"achieved_gbs": height * row_bytes / (e2e_step_ms * 1e-3) / 1e9, "ceiling_gbs": pcie_sum,
+                         "frac": height * row_bytes / (e2e_step_ms * 1e-3) / 1e9 / pcie_sum, "rank0_alone_gbs": pcie_own},
+                "note": "per frame: every rank renders its row blocks and copies them into ONE shared pinned host frame "
+                        "(POSIX shm, cudaHostRegister in every rank) over its own PCIe link; barrier; rank 0 reads the frame; "
+                        "barrier.  ms_per_step is the latency of one gathered frame in host memory"},
+        "gpu_launches": steps * world * launches_per_step,
+        "gathered_frame_verified": verified,
+        "gathered_frame_check": "sha256 of rank 0's device frame == the oracle's committed hash for this configuration",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="measure this workload alone (default: c5 plus the `also` sub-records)")
+    ap.add_argument("--mode", default="frames", choices=["frames", "bands"],
+                    help="with --workload and N>1: 'frames' = each rank renders whole frames (weak); 'bands' = one frame "
+                         "split into interleaved row blocks (strong)")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="bands: 'peer' = kernels store into rank 0's frame through CUDA-IPC peer memory over NVLink; "
+                         "'nccl' = dist.gather of the bands")
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-l2-flush", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="default run without the sub-records")
+    args = ap.parse_args()
+    workload = args.workload or DEFAULT_WORKLOAD
+
+    if args.impl == "reference":
+        run_reference(args, workload)
+        return
+    if args.warmup < 3:
+        args.warmup = 3   # timing rule: at least 3 warm-up steps
+
+    job = Job(args)
+    rank, world = job.rank, job.world
+    if args.mode == "bands" and workload == "c5":
+        raise SystemExit("bench.py: c5 is the frame-sharded orbit sweep; use --mode frames")
+    if args.mode == "bands" and world > 1:
+        out = measure_bands(job, workload, args.steps, args.warmup, args.gather)
+    else:
+        out = measure_frames(job, workload, args.steps, args.warmup, cpu_baseline=(world == 1 and not args.no_cpu_baseline))
+    also = {}
+    if args.workload is None and not args.no_also:
+        def sub(name, rec):
+            if rec is not None:
+                for k in ("metric", "unit", "higher_is_better", "vs_baseline", "dtype", "data"):
+                    rec.pop(k, None)
+                also[name] = rec
+        sub("c2", measure_frames(job, "c2", args.steps, args.warmup))
+        if world == 1:
+            sub("c4", measure_frames(job, "c4", max(3, min(args.steps, 20)), args.warmup))
+        else:
+            sub("c4_bands", measure_bands(job, "c4", max(3, min(args.steps, 20)), args.warmup))
+    clocks = job.sampler.stop(job.windows) if job.sampler else None
+    if rank == 0:
+        out["also"] = also or None
+        out["clocks"] = clocks
         print(json.dumps(out))
     if world > 1:
-        dist.destroy_process_group()
+        job.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -187,13 +187,14 @@ int rt_render_sweep_rgb(const rt_scene *s, const rt_camera *cameras, uint32_t n_
                         uint32_t width, uint32_t height, uint32_t spp,
                         rt_frame_callback cb, void *user, rt_stats *stats);
 
-/* Whole frame on ngpu GPUs of this process (devices 0..ngpu-1): the scene is
- * replicated, GPU g renders blocks of 16 consecutive rows ngpu blocks apart
- * (whole cull tiles stay together) and its kernels store the pixels directly into
- * GPU 0's frame through peer memory (NVLink); without peer access GPU g renders
- * rows g, g+ngpu, ... and the bands are gathered by strided copies.  The
- * frame is then copied to rgba_out (host).  scenes[g] must live on device g.  Replaces the
- * thread pool + sync_channel of Renderer::render (render.rs:271-307). */
+/* Whole frame on ngpu GPUs of this process: the scene is replicated (scenes[g], all distinct, each on its
+ * own device) and GPU g renders blocks of 16 consecutive rows, ngpu blocks apart (whole cull tiles stay
+ * together; interleaving balances the uneven flake).  rgba_out in HOST memory (pinned for full speed): every
+ * GPU copies its own blocks straight into it over its own PCIe link, all links in parallel -- the host frame
+ * is where the bands meet, nothing is gathered on a GPU.  rgba_out in DEVICE memory of scenes[0]'s GPU: the
+ * kernels of the other GPUs store their pixels into it through peer memory (NVLink) -- the stores are the
+ * gather; without peer access GPU g renders rows g, g+ngpu, ... and a strided peer copy de-interleaves them.
+ * Replaces the thread pool + sync_channel of Renderer::render (render.rs:271-307). */
 int rt_render_frame_multi(rt_scene *const *scenes, int ngpu, const rt_camera *camera,
                           uint32_t width, uint32_t height, uint32_t spp,
                           uint8_t *rgba_out, size_t rgba_len, rt_stats *stats);
@@ -252,12 +253,24 @@ int rt_ipc_open(const uint8_t handle[64], void **out);
 int rt_ipc_close(void *p);
 /* cudaMemcpy(dst, src, bytes, cudaMemcpyDefault) for buffers obtained above. */
 int rt_memcpy(void *dst, const void *src, size_t bytes);
+/* cudaMemcpy2DAsync(..., cudaMemcpyDefault, stream): `rows` runs of `width_bytes`, dpitch / spitch apart -- how a
+ * rank copies its interleaved row blocks out of a frame-shaped device buffer into a (shared, pinned) host frame. */
+int rt_memcpy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes, size_t rows,
+                      void *stream);
 
 /* Pinned host memory for output buffers (what the CLI hands to rt_render_frame so
  * the device-to-host copy runs at full PCIe rate).  Replaces the Vec<u8> of
  * RGBABuffer::new (render.rs:80-85). */
 int rt_host_alloc(size_t bytes, void **out);
 void rt_host_free(void *p);
+/* Page-lock host memory the caller already owns (e.g. a frame in a shared-memory segment that several
+ * processes, one per GPU, copy their row blocks into); portable across devices. */
+int rt_host_register(void *p, size_t bytes);
+int rt_host_unregister(void *p);
+/* Diagnostics: copy-only device-to-host rate (GB/s) of the current device into pinned host memory
+ * (`write_combined` != 0: cudaHostAllocWriteCombined) -- the ceiling of every end-to-end number whose frames
+ * leave the GPU; `iters` copies of `bytes` back to back, CUDA events. */
+int rt_microbench_d2h(size_t bytes, int iters, int write_combined, double *gb_per_s);
 
 #ifdef __cplusplus
 }

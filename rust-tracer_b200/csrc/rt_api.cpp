@@ -829,25 +829,32 @@ int rt_render_sweep_rgb(const rt_scene *s, const rt_camera *cameras, uint32_t n_
 
 // Body of rt_render_frame_multi once every scene's scratch is locked.  `launched` records the GPUs that have
 // work in flight, so that the caller can drain them whatever happens here.
+//
+// GPU g renders blocks of 16 consecutive rows, G blocks apart (whole cull tiles stay contiguous in the image).
+//  * HOST output (the CLI's sink): every GPU renders its blocks at their image rows of its OWN frame buffer and
+//    then copies just those blocks to the caller's buffer over its own PCIe link (one strided copy per GPU, all
+//    links in parallel).  Nothing is gathered on a GPU: the host frame is where the bands meet.  An 8K RGBA
+//    frame is 133 MB -- 2.5 ms over one link, against 0.7 ms of rendering on 8 GPUs.
+//  * DEVICE output (a frame on GPU 0, e.g. for a device-side consumer): the kernels of GPU g > 0 store their
+//    pixels straight into that frame through peer memory over NVLink -- the stores are the gather.  Without
+//    peer access GPU g renders rows g, g+G, ... into a band of its own and a strided peer copy de-interleaves it.
 static int frame_multi_locked(rt_scene *const *scenes, int ngpu, const rt_camera *camera, uint32_t width, uint32_t height,
                               uint32_t spp, uint8_t *rgba_out, rt_stats *stats, std::vector<char> &launched) {
     const double t0 = now_ms();
     const size_t row_bytes = (size_t)width * 4;
     rt_scene *root = scenes[0];
-    // The gathered frame lives on GPU 0; GPU 0's own band is rendered straight into it.
-    {
-        DeviceGuard guard(root->device);
-        int rc = ensure(&root->d_frame, &root->d_frame_cap, row_bytes * height);
-        if (rc != RT_OK) return rc;
-    }
-    uint8_t *frame = root->d_frame;
+    int out_dev = -1;
+    const bool to_device = is_device_ptr(rgba_out, &out_dev);
+    if (to_device && out_dev != root->device) return fail(RT_ERR_INVALID, "a device rgba_out must live on the first scene's GPU (%d), not %d", root->device, out_dev);
+    uint8_t *frame = to_device ? rgba_out : nullptr;  // the gathered device frame (device output only)
     uint32_t launches = 0, used = 0;
+    const uint32_t B = 16;
     for (int g = 0; g < ngpu; g++) {
         rt_scene *s = scenes[g];
         DeviceGuard guard(s->device);
         if (!guard.ok) return fail(RT_ERR_CUDA, "cannot select device %d", s->device);
-        bool peer = g == 0;
-        if (g > 0) {
+        bool peer = g == 0 || !to_device;
+        if (to_device && g > 0) {
             int can = 0;
             CUDA_TRY(cudaDeviceCanAccessPeer(&can, s->device, root->device));
             if (can) {
@@ -859,10 +866,8 @@ static int frame_multi_locked(rt_scene *const *scenes, int ngpu, const rt_camera
         }
         rt::RenderParams p;
         uint32_t rows;
+        const uint32_t first = (uint32_t)g * B, stride = (uint32_t)ngpu * B;
         if (peer) {
-            // GPU g renders blocks of 16 consecutive rows, G blocks apart (whole cull tiles stay contiguous
-            // in the image), and stores them at their image rows in GPU 0's frame: over NVLink for g > 0
-            const uint32_t B = 16, first = (uint32_t)g * B, stride = (uint32_t)ngpu * B;
             rows = 0;
             for (uint64_t y0 = first; y0 < height; y0 += stride) rows += (uint32_t)std::min<uint64_t>(B, height - y0);
             if (rows == 0) continue;
@@ -870,7 +875,13 @@ static int frame_multi_locked(rt_scene *const *scenes, int ngpu, const rt_camera
             layout.block_shift = 4;
             layout.out_abs = true;
             fill_params(s, camera, width, height, spp, first, stride, rows, p, layout);
-            p.out = frame;
+            if (to_device) {
+                p.out = frame;
+            } else {
+                int rc = ensure(&s->d_frame, &s->d_frame_cap, row_bytes * height);
+                if (rc != RT_OK) return rc;
+                p.out = s->d_frame;
+            }
             p.pitch = row_bytes;
         } else {
             rows = (height > (uint32_t)g) ? (height - g + ngpu - 1) / ngpu : 0;
@@ -890,8 +901,15 @@ static int frame_multi_locked(rt_scene *const *scenes, int ngpu, const rt_camera
         launches += (uint32_t)launches_per_frame(p);
         if (g == 0) used = variant_used(p);
         if (stats) CUDA_TRY(cudaEventRecord(s->ev1, s->own_stream));
-        if (!peer)  // no peer access: strided copy, the pitch de-interleaves the band into the frame
+        if (!to_device) {
+            // this GPU's blocks -> the host frame: whole blocks as one strided copy, then the partial last block
+            const size_t blk = (size_t)B * row_bytes, pitch = (size_t)stride * row_bytes, off = (size_t)first * row_bytes;
+            const uint32_t whole = rows / B, tail = rows % B;
+            if (whole) CUDA_TRY(cudaMemcpy2DAsync(rgba_out + off, pitch, s->d_frame + off, pitch, blk, whole, cudaMemcpyDeviceToHost, s->own_stream));
+            if (tail) CUDA_TRY(cudaMemcpyAsync(rgba_out + off + (size_t)whole * pitch, s->d_frame + off + (size_t)whole * pitch, (size_t)tail * row_bytes, cudaMemcpyDeviceToHost, s->own_stream));
+        } else if (!peer) {  // no peer access: strided copy, the pitch de-interleaves the band into the frame
             CUDA_TRY(cudaMemcpy2DAsync(frame + row_bytes * g, row_bytes * ngpu, s->d_fb, row_bytes, row_bytes, rows, cudaMemcpyDefault, s->own_stream));
+        }
     }
     double kmax = 0.0;
     for (int g = ngpu - 1; g >= 0; g--) {
@@ -903,10 +921,6 @@ static int frame_multi_locked(rt_scene *const *scenes, int ngpu, const rt_camera
             CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
             if (ms > kmax) kmax = ms;
         }
-    }
-    {
-        DeviceGuard guard(root->device);
-        CUDA_TRY(cudaMemcpy(rgba_out, frame, row_bytes * height, cudaMemcpyDefault));
     }
     if (stats) {
         stats->kernel_ms = kmax;
@@ -1240,6 +1254,57 @@ int rt_ipc_close(void *p) {
 int rt_memcpy(void *dst, const void *src, size_t bytes) {
     if (!dst || !src) return fail(RT_ERR_INVALID, "NULL argument");
     CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
+    return RT_OK;
+}
+
+int rt_memcpy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes, size_t rows, void *stream) {
+    if (!dst || !src) return fail(RT_ERR_INVALID, "NULL argument");
+    if (width_bytes == 0 || rows == 0) return RT_OK;
+    CUDA_TRY(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, rows, cudaMemcpyDefault, (cudaStream_t)stream));
+    return RT_OK;
+}
+
+int rt_host_register(void *p, size_t bytes) {
+    if (!p || !bytes) return fail(RT_ERR_INVALID, "NULL argument");
+    if (rt_device_count() == 0) return fail(RT_ERR_CUDA, "no CUDA device");
+    CUDA_TRY(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return RT_OK;
+}
+
+int rt_host_unregister(void *p) {
+    if (!p) return RT_OK;
+    CUDA_TRY(cudaHostUnregister(p));
+    return RT_OK;
+}
+
+// Copy-only microbenchmark of the link the end-to-end numbers are bound by: `iters` device-to-host copies of
+// `bytes` from the current device into pinned host memory, back to back on one stream, timed with CUDA events.
+int rt_microbench_d2h(size_t bytes, int iters, int write_combined, double *gb_per_s) {
+    if (!gb_per_s || bytes == 0 || iters < 1) return fail(RT_ERR_INVALID, "bad argument");
+    if (rt_device_count() == 0) return fail(RT_ERR_CUDA, "no CUDA device");
+    uint8_t *d = nullptr, *h = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    float ms = 0.0f;
+    cudaError_t e = cudaMalloc(&d, bytes);
+    if (e == cudaSuccess) e = cudaMemset(d, 0x5a, bytes);
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&h, bytes, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st);  // warm-up
+    if (e == cudaSuccess) e = cudaEventRecord(e0, st);
+    for (int i = 0; i < iters && e == cudaSuccess; i++) e = cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaEventRecord(e1, st);
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    if (h) cudaFreeHost(h);
+    if (d) cudaFree(d);
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, "d2h microbench: %s", cudaGetErrorString(e));
+    *gb_per_s = (double)bytes * iters / (ms * 1e-3) / 1e9;
     return RT_OK;
 }
 

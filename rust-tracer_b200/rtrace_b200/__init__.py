@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "rt_scene_counts", "rt_scene_export_nodes", "rt_flatten_pyramid_host", "rt_scene_light", "rt_scene_eye",
     "rt_scene_device", "rt_render_region", "rt_render_preview", "rt_render_rows", "rt_render_row_blocks", "rt_render_frame", "rt_render_sweep", "rt_render_sweep_rgb",
     "rt_render_frame_multi", "rt_render_sweep_multi",
-    "rt_count_rays", "rt_trace_rays", "rt_measure_fp32_peak", "rt_microbench_fp32", "rt_selftest_math", "rt_debug_phased_tiles", "rt_host_alloc", "rt_host_free", "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_memcpy",
+    "rt_count_rays", "rt_trace_rays", "rt_measure_fp32_peak", "rt_microbench_fp32", "rt_selftest_math", "rt_debug_phased_tiles", "rt_host_alloc", "rt_host_free", "rt_host_register", "rt_host_unregister", "rt_microbench_d2h", "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_memcpy", "rt_memcpy2d_async",
 ]
 
 
@@ -101,8 +101,12 @@ def lib():
     L.rt_ipc_open.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.rt_ipc_close.argtypes = [vp]
     L.rt_memcpy.argtypes = [vp, vp, C.c_size_t]
+    L.rt_memcpy2d_async.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp]
     L.rt_host_free.argtypes = [vp]
     L.rt_host_free.restype = None
+    L.rt_host_register.argtypes = [vp, C.c_size_t]
+    L.rt_host_unregister.argtypes = [vp]
+    L.rt_microbench_d2h.argtypes = [C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -390,6 +394,21 @@ def microbench_fp32(device, mode):
     return t.value
 
 
+def microbench_d2h(nbytes, iters=20, write_combined=False):
+    """Copy-only device-to-host rate of the current device into pinned host memory, GB/s."""
+    g = C.c_double()
+    _check(lib().rt_microbench_d2h(nbytes, iters, 1 if write_combined else 0, C.byref(g)))
+    return g.value
+
+
+def host_register(ptr, nbytes):
+    _check(lib().rt_host_register(C.c_void_p(ptr), nbytes))
+
+
+def host_unregister(ptr):
+    _check(lib().rt_host_unregister(C.c_void_p(ptr)))
+
+
 def selftest_math(n=1 << 24, seed=1):
     m = (C.c_uint64 * 6)()
     _check(lib().rt_selftest_math(n, seed, m))
@@ -431,6 +450,10 @@ def ipc_open(handle):
 
 def memcpy(dst, src, nbytes):
     _check(lib().rt_memcpy(C.c_void_p(dst), C.c_void_p(src), nbytes))
+
+
+def memcpy2d_async(dst, dpitch, src, spitch, width_bytes, rows, stream=None):
+    _check(lib().rt_memcpy2d_async(C.c_void_p(dst), dpitch, C.c_void_p(src), spitch, width_bytes, rows, stream))
 
 
 def ipc_close(ptr):
