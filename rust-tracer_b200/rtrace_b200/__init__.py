@@ -15,7 +15,7 @@ PKG_DIR = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("RTRACE_B200_LIB") or os.path.join(PKG_DIR, "librtrace_b200.so")  # env: kernel experiments
 
 RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_NOMEM, RT_ERR_BUFFER = 0, -1, -2, -3, -4
-VARIANT_AUTO, VARIANT_LANE, VARIANT_WARP, VARIANT_TILE, VARIANT_PHASED, VARIANT_PIPE = 0, 1, 2, 3, 4, 5
+VARIANT_AUTO, VARIANT_LANE, VARIANT_WARP, VARIANT_TILE, VARIANT_PHASED, VARIANT_FUSED = 0, 1, 2, 3, 4, 5
 
 # every symbol include/rtrace.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
@@ -57,6 +57,17 @@ def lib():
     if not os.path.exists(LIB_PATH):
         raise ImportError("%s is missing: run `make lib` (or __graft_entry__.build()); there is no fallback" % LIB_PATH)
     L = C.CDLL(LIB_PATH)
+    if os.environ.get("RTRACE_B200_LIB"):   # an experiment build may predate newer entry points: bind what it has
+        class _Tolerant:
+            def __init__(self, real):
+                object.__setattr__(self, "_real", real)
+
+            def __getattr__(self, name):
+                try:
+                    return getattr(self._real, name)
+                except AttributeError:
+                    return type("_Missing", (), {"argtypes": None, "restype": None})()
+        real, L = L, _Tolerant(L)
     vp, u32, u16, f32p, u8p = C.c_void_p, C.c_uint32, C.c_uint16, C.POINTER(C.c_float), C.c_void_p
     u64p, u32p = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
     L.rt_last_error.restype = C.c_char_p
@@ -107,6 +118,8 @@ def lib():
     L.rt_host_register.argtypes = [vp, C.c_size_t]
     L.rt_host_unregister.argtypes = [vp]
     L.rt_microbench_d2h.argtypes = [C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    if os.environ.get("RTRACE_B200_LIB"):
+        L = real
     _lib = L
     return L
 
