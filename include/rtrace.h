@@ -72,8 +72,7 @@ enum {
     RT_VARIANT_LANE = 1,  /* one thread per pixel, per-lane skip-pointer traversal      */
     RT_VARIANT_WARP = 2,  /* warp-cooperative traversal (ballot/shuffle)                */
     RT_VARIANT_TILE = 3,  /* tile beam-culling + candidate lists, one fused kernel      */
-    RT_VARIANT_PHASED = 4, /* the same algorithm as four homogeneous launches on one stream */
-    RT_VARIANT_FUSED = 5   /* the same four phases by one persistent warp per cull tile, ONE launch per frame */
+    RT_VARIANT_PHASED = 4 /* the same algorithm as four homogeneous launches on one stream */
 };
 
 /* ---- library ------------------------------------------------------------ */

@@ -65,9 +65,7 @@ struct rt_scene {
     cudaStream_t copy_stream = nullptr, render2 = nullptr;
     cudaEvent_t sweep_rendered[SWEEP_RING] = {nullptr, nullptr, nullptr}, sweep_copied[SWEEP_RING] = {nullptr, nullptr, nullptr};
     std::map<cudaStream_t, Phased> phased;
-    std::map<cudaStream_t, Phased> fused;  // FUSED variant: per resident warp, not per frame (hdr unused)
-    uint32_t fused_blocks = 0;             // persistent grid of the FUSED variant on this device
-    std::mutex mu_phased;  // guards the maps only (mu may already be held by the caller)
+    std::mutex mu_phased;  // guards the map only (mu may already be held by the caller)
 };
 
 namespace {
@@ -267,8 +265,6 @@ int kernel_variant(const rt::RenderParams &p) {
             return tile_ok ? RT_KERNEL_TILE : RT_KERNEL_LANE;
         case RT_VARIANT_PHASED:
             return tile_ok ? RT_KERNEL_PHASED : RT_KERNEL_LANE;
-        case RT_VARIANT_FUSED:
-            return tile_ok ? RT_KERNEL_FUSED : RT_KERNEL_LANE;
         default:
             break;
     }
@@ -328,42 +324,10 @@ int prepare_phased(rt_scene *s, rt::RenderParams &p, cudaStream_t stream) {
     return RT_OK;
 }
 
-// Scratch of the FUSED variant for this stream: per resident warp of the persistent grid (independent of the
-// frame size), allocated on first use.
-int prepare_fused(rt_scene *s, rt::RenderParams &p, cudaStream_t stream) {
-    size_t wb = 0;
-    uint32_t blocks = 0, units = 0;
-    rt_fused_scratch(p.spp, &blocks, &wb, &units);
-    const char *cap = getenv("RTRACE_POOL_UNITS");  // tests: a tiny per-warp pool exercises the overflow fallback
-    if (cap && *cap) units = (uint32_t)strtoul(cap, nullptr, 10);
-    std::lock_guard<std::mutex> lock(s->mu_phased);
-    rt_scene::Phased &ph = s->fused[stream];
-    int rc = ensure_typed(&ph.winner, &ph.winner_cap, wb);
-    const size_t pool_bytes = (size_t)blocks * 4 * units * sizeof(uint4);
-    if (rc == RT_OK) {
-        size_t have = (size_t)ph.pool_units * sizeof(uint4);
-        rc = ensure_typed(&ph.pool, &have, pool_bytes ? pool_bytes : sizeof(uint4));
-        if (rc == RT_OK) ph.pool_units = (uint32_t)(have / sizeof(uint4));
-    }
-    if (rc == RT_OK && !ph.pool_count) CUDA_TRY(cudaMalloc(&ph.pool_count, sizeof(uint32_t)));
-    if (rc != RT_OK) return rc;
-    s->fused_blocks = blocks;
-    p.winner = ph.winner;
-    p.tile_hdr = nullptr;
-    p.pool = ph.pool;
-    p.pool_cap = units;  // per warp
-    p.pool_count = ph.pool_count;  // the frame's tile counter
-    return RT_OK;
-}
-
 int launch(rt_scene *s, rt::RenderParams &p, bool diag, cudaStream_t stream) {
     const int v = kernel_variant(p);
     cudaError_t e;
-    if (v == RT_KERNEL_FUSED) {
-        int rc = prepare_fused(s, p, stream);
-        if (rc != RT_OK) return rc;
-        e = rt_launch_render_fused(diag, p, stream, s->fused_blocks);
-    } else if (v == RT_KERNEL_PHASED) {
+    if (v == RT_KERNEL_PHASED) {
         int rc = prepare_phased(s, p, stream);
         if (rc != RT_OK) return rc;
         e = rt_launch_render_phased(diag, p, stream, tile_shape());
@@ -406,7 +370,7 @@ int rt_set_device(int device) {
 }
 
 int rt_set_variant(int variant) {
-    if (variant < RT_VARIANT_AUTO || variant > RT_VARIANT_FUSED) return fail(RT_ERR_INVALID, "unknown variant %d", variant);
+    if (variant < RT_VARIANT_AUTO || variant > RT_VARIANT_PHASED) return fail(RT_ERR_INVALID, "unknown variant %d", variant);
     g_variant = variant;
     return RT_OK;
 }
@@ -486,13 +450,12 @@ void rt_scene_destroy(rt_scene *s) {
         }
         if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
         if (s->render2) cudaStreamDestroy(s->render2);
-        for (auto *m : {&s->phased, &s->fused})
-            for (auto &kv : *m) {
-                if (kv.second.winner) cudaFree(kv.second.winner);
-                if (kv.second.hdr) cudaFree(kv.second.hdr);
-                if (kv.second.pool) cudaFree(kv.second.pool);
-                if (kv.second.pool_count) cudaFree(kv.second.pool_count);
-            }
+        for (auto &kv : s->phased) {
+            if (kv.second.winner) cudaFree(kv.second.winner);
+            if (kv.second.hdr) cudaFree(kv.second.hdr);
+            if (kv.second.pool) cudaFree(kv.second.pool);
+            if (kv.second.pool_count) cudaFree(kv.second.pool_count);
+        }
     }
     delete s;
 }

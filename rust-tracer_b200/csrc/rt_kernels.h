@@ -4,7 +4,7 @@
 #include <stddef.h>
 #include <stdint.h>
 
-enum { RT_KERNEL_LANE = 1, RT_KERNEL_WARP = 2, RT_KERNEL_TILE = 3, RT_KERNEL_PHASED = 4, RT_KERNEL_FUSED = 5 };
+enum { RT_KERNEL_LANE = 1, RT_KERNEL_WARP = 2, RT_KERNEL_TILE = 3, RT_KERNEL_PHASED = 4 };
 
 namespace rt {
 struct RenderParams;
@@ -27,8 +27,3 @@ cudaError_t rt_launch_math_selftest(uint32_t n, uint32_t seed, unsigned long lon
 void rt_phased_scratch(uint32_t width, uint32_t rows, uint32_t spp, int shape, size_t *winner_bytes, size_t *hdr_bytes,
                        uint32_t *pool_units);
 cudaError_t rt_launch_render_phased(bool diag, const rt::RenderParams &p, cudaStream_t stream, int shape);
-
-// FUSED variant (rt_phased.cu): the same four phases run by one persistent warp per cull tile in ONE launch.
-// `blocks` = persistent grid size; scratch is per resident warp, not per frame.
-void rt_fused_scratch(uint32_t spp, uint32_t *blocks, size_t *winner_bytes, uint32_t *pool_units_per_warp);
-cudaError_t rt_launch_render_fused(bool diag, const rt::RenderParams &p, cudaStream_t stream, uint32_t blocks);

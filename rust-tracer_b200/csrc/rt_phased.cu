@@ -27,14 +27,6 @@
 //                     accumulation in reference sample order, RGBA8 quantisation,
 //                     one framebuffer store per pixel (pair).
 //
-// FUSED variant (fused_tile_kernel, below): the same four phases run by ONE persistent warp per cull
-// tile, back to back -- cull, test its pixel tiles, shadow cull, shade its pixel tiles -- with grid =
-// SMs x resident blocks and tiles handed out by an atomic counter.  Nothing crosses a launch boundary:
-// candidate chunks and winners live in a per-warp scratch slice that stays in L1/L2 and is reused for
-// the next tile, there are no launch tails except the last tile of each warp, and the 32 resident
-// warps of an SM are in different phases at any time (culls are latency chains, tests and shading are
-// throughput work), so they fill one another's stalls.
-//
 // Every pre-filter keeps a superset of what the exact test can accept (the worst-case
 // f32 error of the discriminant is folded into the radii); the exact tests are the
 // reference's operations one by one, so the bytes are the oracle's.  A cull tile whose
@@ -78,10 +70,7 @@ struct CullShared {
 // Geometry shared by the four phases.
 template <int SPP, int PXW, int PXH, int CW, int CH>
 struct Geo {
-    static constexpr int SPP_ = SPP, PXW_ = PXW, PXH_ = PXH, CW_ = CW, CH_ = CH;
     static constexpr int NPX = PXW * PXH, NS = SPP * SPP, S = NPX * NS;
-    static constexpr bool WDIST = NS == 1;                         // winners carry their hit distance (see test_tile)
-    static constexpr uint32_t WINNER_WORDS = S * 32 * (WDIST ? 2 : 1);  // 32-bit words of winner scratch per pixel tile
     static constexpr float FRAC = (float)(SPP - 1) / (float)SPP;  // largest sub-sample offset
     static constexpr int TW = 8 * PXW, TH = 4 * PXH;  // pixel tile (one warp)
     static constexpr int BW = TW * CW, BH = TH * CH;  // cull tile
@@ -156,33 +145,6 @@ RT_DEV void stage_wait() { asm volatile("cp.async.commit_group;\ncp.async.wait_g
 static constexpr uint32_t PU = 4;  // 16-byte units per primary candidate record
 static constexpr uint32_t SU = 3;  // 16-byte units per shadow candidate record
 
-// Who shares a cull tile's staged chunk and synchronises around it: the four warps of a block (PHASED: one
-// block per cull tile, one warp per pixel tile) or one warp alone (FUSED: a warp walks its cull tile's pixel
-// tiles one after the other).  STAGED = candidates of the first chunk held in shared memory.
-struct BlockPol {
-    static constexpr uint32_t STAGED = T_CAND;
-    RT_DEV static void sync() { __syncthreads(); }
-    RT_DEV static uint32_t tid() { return threadIdx.x; }
-    RT_DEV static uint32_t nthreads() { return blockDim.x; }
-    // chunks were written by an earlier launch: read-only here, the non-coherent path is safe (and lets the
-    // compiler batch the loads)
-    RT_DEV static uint4 ld(const uint4 *q) { return __ldg(q); }
-};
-struct WarpPol {
-    static constexpr uint32_t STAGED = 64;  // 1 + PU * 64 units = 4112 bytes: fits the warp's CullShared, which it aliases
-    RT_DEV static void sync() { __syncwarp(); }
-    RT_DEV static uint32_t tid() { return threadIdx.x & 31u; }
-    RT_DEV static uint32_t nthreads() { return 32u; }
-    // chunks are written and read inside one kernel, and their units are reused tile after tile: plain
-    // (coherent) loads -- ld.global.nc could return a previous tile's line
-    RT_DEV static uint4 ld(const uint4 *q) { return *q; }
-};
-
-// FUSED: a warp's private slice of the candidate pool, refilled for every cull tile (no atomics).
-struct PrivPool {
-    uint32_t base, cap, used;
-};
-
 // Append the warp's candidate list to the pool as a chunk {count, next} + records, chained in
 // front of `head`.  The exact-test operands are stored as broadcast PAIRS so that the packed f32x2
 // tests of K2 / K4 (two rays per instruction) load them straight into register pairs:
@@ -190,18 +152,8 @@ struct PrivPool {
 //   shadow  (SU units): {cx,cx,cy,cy} {cz,cz,r*r,r*r} {c.e1, c.e2, R^2, 0}
 // The last unit of each record is what the per-lane pre-filters read: the image-space box of the
 // rays that can hit (screen_box), and the candidate's disc in the plane perpendicular to the light.
-RT_DEV uint32_t flush_reserve(const RenderParams &p, int lane, uint32_t n, uint32_t rec_units, uint32_t head, bool &ok,
-                              PrivPool *priv) {
+RT_DEV uint32_t flush_reserve(const RenderParams &p, int lane, uint32_t n, uint32_t rec_units, uint32_t head, bool &ok) {
     const uint32_t units = 1u + rec_units * n;
-    if (priv) {  // the warp's own slice: plain bump allocation (uniform across the warp)
-        const uint32_t at = priv->base + priv->used;
-        ok = priv->used + units <= priv->cap;
-        if (ok) {
-            priv->used += units;
-            if (lane == 0) p.pool[at] = make_uint4(n, head, 0u, 0u);
-        }
-        return at;
-    }
     // A reservation that starts past the capacity is handed back, so once the pool is exhausted the counter hovers
     // at pool_cap + (reservations in flight) and can never wrap past 2^32 and hand out units that alias live
     // chunks (pool_cap <= 2^26; the API allows 65535 x 65535 frames).  The comparison is 64-bit.  (Reading the
@@ -217,10 +169,10 @@ RT_DEV uint32_t flush_reserve(const RenderParams &p, int lane, uint32_t n, uint3
     if (ok && lane == 0) p.pool[base] = make_uint4(n, head, 0u, 0u);
     return base;
 }
-RT_DEV uint32_t flush_primary(const RenderParams &p, CullShared &sm, int lane, uint32_t n, uint32_t head, PrivPool *priv = nullptr) {
+RT_DEV uint32_t flush_primary(const RenderParams &p, CullShared &sm, int lane, uint32_t n, uint32_t head) {
     if (n == 0 || head == OVERFLOWED) return head;
     bool ok;
-    const uint32_t base = flush_reserve(p, lane, n, PU, head, ok, priv);
+    const uint32_t base = flush_reserve(p, lane, n, PU, head, ok);
     if (!ok) return OVERFLOWED;
     // Records are written front to back by a lower bound of the distance the exact test can return.  With
     // disc_f32 <= disc + eps (eps = EPS_DISC (v.v + r*r), rt_cull.cuh) the f32 root b - sqrt(disc_f32) is smallest
@@ -252,11 +204,10 @@ RT_DEV uint32_t flush_primary(const RenderParams &p, CullShared &sm, int lane, u
     }
     return base;
 }
-RT_DEV uint32_t flush_shadow(const RenderParams &p, const CullShared &sm, const ShadowBeam &B, int lane, uint32_t n, uint32_t head,
-                             PrivPool *priv = nullptr) {
+RT_DEV uint32_t flush_shadow(const RenderParams &p, const CullShared &sm, const ShadowBeam &B, int lane, uint32_t n, uint32_t head) {
     if (n == 0 || head == OVERFLOWED) return head;
     bool ok;
-    const uint32_t base = flush_reserve(p, lane, n, SU, head, ok, priv);
+    const uint32_t base = flush_reserve(p, lane, n, SU, head, ok);
     if (!ok) return OVERFLOWED;
     for (uint32_t c = lane; c < n; c += 32) {
         const float4 a = sm.cand4[c];  // {c, r*r}
@@ -317,21 +268,24 @@ __global__ void __launch_bounds__(32 * P_WARPS) phase_cull_primary(const RenderP
 // ---------------------------------------------------------------------------
 // K2: exact closest-hit tests, one warp per pixel tile
 // ---------------------------------------------------------------------------
-// The primary candidates of cull tile chain `head` (not NO_CHUNK) against pixel tile (pt_x, pt_y): writes the
-// winner of every sample slot to `winner` and folds the tile's hit distances into tmin / tmax (per lane).
-// `stage` holds (or is about to hold: the cp.async copy may still be in flight, it is awaited here) the first
-// POL::STAGED candidates of the first chunk, shared by the threads POL synchronises.
-template <class G, class POL>
-RT_DEV void test_tile(const RenderParams &p, const uint4 *stage, const uint32_t head, const uint32_t pt_x, const uint32_t pt_y,
-                      uint32_t *winner, const int lane, float &tmin, float &tmax) {
-    constexpr int SPP = G::SPP_, PXW = G::PXW_, PXH = G::PXH_;
+template <int SPP, int PXW, int PXH, int CW, int CH>
+__global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phase_test_primary(const RenderParams p) {
+    using G = Geo<SPP, PXW, PXH, CW, CH>;
     constexpr int S = G::S, NS = G::NS;
+    __shared__ uint4 stage[1 + PU * T_CAND];  // the cull tile's first candidate chunk, shared by its pixel tiles
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const G geo(p.width, p.row_count);
+    // one block per cull tile, one warp per pixel tile of it
+    const uint32_t ct = blockIdx.y * geo.ctiles_x + blockIdx.x;  // 2-D grid of cull tiles: no division
+    const uint32_t pt_x = blockIdx.x * CW + (uint32_t)(warp % CW), pt_y = blockIdx.y * CH + (uint32_t)(warp / CW);
+    const uint32_t pt = pt_y * geo.ptiles_x + pt_x;
     const uint32_t tile_x0 = pt_x * G::TW, tile_j0 = pt_y * G::TH;
     const V3 eye = v3(p.eye[0], p.eye[1], p.eye[2]);
     const ONE2 one = f2s(p.one);  // 1.0f the compiler cannot see (rt_pack.cuh)
     // one sample per pixel: the winner's distance travels with its index (8 bytes per sample, still L2-resident at 4K);
-    // supersampled frames keep 4 bytes per sample and K4 recomputes the distance
-    constexpr bool WDIST = G::WDIST;
+    // supersampled frames keep 4 bytes per sample (their winners stream through HBM) and K4 recomputes the distance
+    constexpr bool WDIST = NS == 1;
+    uint32_t *winner = p.winner + (size_t)pt * S * 32 * (WDIST ? 2 : 1);
     auto put_winner = [&](int s, uint32_t idx, float dist) {
         if (WDIST) reinterpret_cast<uint2 *>(winner)[s * 32 + lane] = make_uint2(idx, __float_as_uint(dist));
         else winner[s * 32 + lane] = idx;
@@ -340,11 +294,22 @@ RT_DEV void test_tile(const RenderParams &p, const uint4 *stage, const uint32_t 
     uint32_t bx, bj;  // first pixel of this lane's block
     slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, 0, bx, bj);
     const bool lane_in = bx < p.width && bj < p.row_count;
-    constexpr uint32_t STAGED_UNITS = 1u + PU * POL::STAGED;
-    auto fetch = [&](uint32_t base, uint32_t off) {
-        if (POL::STAGED >= (uint32_t)T_CAND) return base == head ? stage[off] : POL::ld(&p.pool[base + off]);  // whole first chunk staged
-        return (base == head && off < STAGED_UNITS) ? stage[off] : POL::ld(&p.pool[base + off]);
-    };
+    const uint32_t head = p.tile_hdr[ct].x;
+    if (head == NO_CHUNK) return;  // no candidate at all: K4 sees an empty hit range and never reads the winners
+    const bool staged = head != OVERFLOWED;
+    if (staged) {  // stage the first chunk (almost always the only one) in shared memory, asynchronously
+        const uint32_t units = 1u + PU * __ldg(&p.pool[head]).x;
+        for (uint32_t u = threadIdx.x; u < units; u += blockDim.x) stage_async(&stage[u], &p.pool[head + u]);
+    }
+    if (pt_x >= geo.ptiles_x || pt_y >= geo.ptiles_y) {  // cull tile on the frame edge: only the block's barrier is left to do
+        if (staged) {
+            stage_wait();
+            __syncthreads();
+        }
+        return;
+    }
+    auto fetch = [&](uint32_t base, uint32_t off) { return base == head ? stage[off] : __ldg(&p.pool[base + off]); };
+    float tmin = RT_INF, tmax = 0.0f;
 
     if (head == OVERFLOWED) {  // pool exhausted for this cull tile: the per-lane walk (group.rs:72-83)
         for (int s = 0; s < S; s++) {
@@ -360,162 +325,129 @@ RT_DEV void test_tile(const RenderParams &p, const uint4 *stage, const uint32_t 
             }
             put_winner(s, bi, hitd);
         }
-        return;
-    }
-    // Sample-coordinate rectangles of this lane's own block and of the warp's pixel tile: a
-    // candidate whose screen_box misses the rectangle cannot be hit by any of its rays.
-    constexpr float frac = G::FRAC;
-    float lx0, lx1, ly0, ly1, wx0, wx1, wy0, wy1;
-    {
-        const uint32_t xh = min(bx + PXW, p.width) - 1u, jh = min(bj + PXH, p.row_count) - 1u;
-        const float ya = (float)(image_row(p, bj)), yb = (float)(image_row(p, jh));
-        lx0 = (float)bx, lx1 = (float)xh + frac, ly0 = fminf(ya, yb), ly1 = fmaxf(ya, yb) + frac;
-    }
-    {
-        const uint32_t xh = min(tile_x0 + G::TW, p.width) - 1u, jh = min(tile_j0 + G::TH, p.row_count) - 1u;
-        const float ya = (float)(image_row(p, tile_j0)), yb = (float)(image_row(p, jh));
-        wx0 = (float)tile_x0, wx1 = (float)xh + frac, wy0 = fminf(ya, yb), wy1 = fmaxf(ya, yb) + frac;
-    }
-    // candidates c0..c1 (at most 32) of a chunk -> bit mask of those this LANE's block can see.
-    // First every lane tests ONE candidate against the warp tile's rectangle (ballot), then each
-    // lane tests the survivors against its own.
-    auto cand_box = [&](uint32_t base, uint32_t c) {
-        const uint4 u = fetch(base, 4u + PU * c);
-        return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
-    };
-    auto chunk_mask = [&](uint32_t base, uint32_t c0, uint32_t c1) {
-        const bool w_ok = (c0 + lane < c1) && box_overlaps(cand_box(base, c0 + lane), wx0, wx1, wy0, wy1);
-        uint32_t mask = 0;
-        for (uint32_t wm = __ballot_sync(FULLMASK, w_ok); wm; wm &= wm - 1u) {
-            const uint32_t c = c0 + (uint32_t)__ffs((int)wm) - 1u;
-            if (box_overlaps(cand_box(base, c), lx0, lx1, ly0, ly1)) mask |= 1u << (c - c0);
+    } else {
+        // Sample-coordinate rectangles of this lane's own block and of the warp's pixel tile: a
+        // candidate whose screen_box misses the rectangle cannot be hit by any of its rays.
+        constexpr float frac = G::FRAC;
+        float lx0, lx1, ly0, ly1, wx0, wx1, wy0, wy1;
+        {
+            const uint32_t xh = min(bx + PXW, p.width) - 1u, jh = min(bj + PXH, p.row_count) - 1u;
+            const float ya = (float)(image_row(p, bj)), yb = (float)(image_row(p, jh));
+            lx0 = (float)bx, lx1 = (float)xh + frac, ly0 = fminf(ya, yb), ly1 = fmaxf(ya, yb) + frac;
         }
-        return lane_in ? mask : 0u;
-    };
-    // One pass covers all of the lane's slots (S <= 4): the staged chunk is awaited after ray generation, so
-    // the copy overlaps it.  With more passes the deferred barrier costs registers (spills under the 64-register
-    // cap), so it is taken up front.
-    constexpr bool LAZY = S <= 4;
-    uint32_t mask0 = 0;  // mask of the first 32 candidates of the first chunk: reused by every slot pair
-    if (!LAZY) {
-        stage_wait();
-        POL::sync();
-        mask0 = chunk_mask(head, 0u, min(stage[0].x, 32u));
-    }
-    // GP packed pairs (two slots each) per pass: every candidate record is loaded once for all of them and
-    // the pairs' dependency chains interleave.
-    constexpr int GP = (S >= 4) ? 2 : 1;
-#pragma unroll 1
-    for (int g0 = 0; g0 < S; g0 += 2 * GP) {
-        V3x2 d[GP];
-        F2 bd[GP];
-        uint32_t bi[GP][2];
-#pragma unroll
-        for (int k = 0; k < GP; k++) {
-            const int s0 = min(g0 + 2 * k, S - 1), s1 = min(s0 + 1, S - 1);  // a pair past the end repeats the last slot
-            uint32_t x0, j0, x1, j1;
-            slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s0 / NS, x0, j0);
-            slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s1 / NS, x1, j1);
-            d[k] = slot_dir2<SPP>(one, p, x0, image_row(p, j0), s0 % NS, x1, image_row(p, j1), s1 % NS);
-            bd[k] = f2s(RT_INF);
-            bi[k][0] = bi[k][1] = NO_HIT;
+        {
+            const uint32_t xh = min(tile_x0 + G::TW, p.width) - 1u, jh = min(tile_j0 + G::TH, p.row_count) - 1u;
+            const float ya = (float)(image_row(p, tile_j0)), yb = (float)(image_row(p, jh));
+            wx0 = (float)tile_x0, wx1 = (float)xh + frac, wy0 = fminf(ya, yb), wy1 = fmaxf(ya, yb) + frac;
         }
-        if (LAZY) {  // the only pass: every thread sharing the stage arrives here exactly once per tile
-            stage_wait();
-            POL::sync();
-            mask0 = chunk_mask(head, 0u, min(stage[0].x, 32u));
-        }
-        auto test = [&](const uint4 u0, const uint4 u1, const uint4 u2) {
-            V3x2 v;
-            v.x = f2(__uint_as_float(u0.x), __uint_as_float(u0.y));
-            v.y = f2(__uint_as_float(u0.z), __uint_as_float(u0.w));
-            v.z = f2(__uint_as_float(u1.x), __uint_as_float(u1.y));
-            const F2 nvv = f2(__uint_as_float(u1.z), __uint_as_float(u1.w));
-            const F2 rr = f2(__uint_as_float(u2.x), __uint_as_float(u2.y));
-            const uint32_t idx = u2.z;
-#pragma unroll
-            for (int k = 0; k < GP; k++) {
-                const F2 dist = primary_distance2(one, v, nvv, rr, d[k]);
-                // primitive.rs:79 + pre-order visiting: strictly closer wins, ties -> lowest index
-                if (dist.x < bd[k].x || (dist.x == bd[k].x && idx < bi[k][0] && bi[k][0] != NO_HIT)) bd[k].x = dist.x, bi[k][0] = idx;
-                if (dist.y < bd[k].y || (dist.y == bd[k].y && idx < bi[k][1] && bi[k][1] != NO_HIT)) bd[k].y = dist.y, bi[k][1] = idx;
-            }
+        // candidates c0..c1 (at most 32) of a chunk -> bit mask of those this LANE's block can see.
+        // First every lane tests ONE candidate against the warp tile's rectangle (ballot), then each
+        // lane tests the survivors against its own.
+        auto cand_box = [&](uint32_t base, uint32_t c) {
+            const uint4 u = fetch(base, 4u + PU * c);
+            return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
         };
-        // farthest distance the lane still has to beat (+inf while one of its slots has no hit)
-        auto held = [&]() {
-            float h = fmaxf(bd[0].x, bd[0].y);
-#pragma unroll
-            for (int k = 1; k < GP; k++) h = fmaxf(h, fmaxf(bd[k].x, bd[k].y));
-            return h;
+        auto chunk_mask = [&](uint32_t base, uint32_t c0, uint32_t c1) {
+            const bool w_ok = (c0 + lane < c1) && box_overlaps(cand_box(base, c0 + lane), wx0, wx1, wy0, wy1);
+            uint32_t mask = 0;
+            for (uint32_t wm = __ballot_sync(FULLMASK, w_ok); wm; wm &= wm - 1u) {
+                const uint32_t c = c0 + (uint32_t)__ffs((int)wm) - 1u;
+                if (box_overlaps(cand_box(base, c), lx0, lx1, ly0, ly1)) mask |= 1u << (c - c0);
+            }
+            return lane_in ? mask : 0u;
         };
-        // hot path: the first 32 candidates of the staged chunk, straight from shared memory; they come
-        // front to back, so the lane is done once a candidate cannot start before what it holds
-        for (uint32_t m = mask0; m; m &= m - 1u) {
-            const uint32_t c = (uint32_t)__ffs((int)m) - 1u;
-            const uint4 u2 = stage[3u + PU * c];
-            if (__uint_as_float(u2.w) > held()) break;
-            test(stage[1u + PU * c], stage[2u + PU * c], u2);
-        }
-        // cold path: the rest of the staged chunk and any further chunks of the chain
-        for (uint32_t base = head; base != NO_CHUNK;) {
-            const uint4 hdr = fetch(base, 0u);
-            const uint32_t n = hdr.x;
-            for (uint32_t c0 = (base == head) ? 32u : 0u; c0 < n; c0 += 32) {
-                for (uint32_t m = chunk_mask(base, c0, min(n, c0 + 32u)); m; m &= m - 1u) {
-                    const uint32_t c = c0 + (uint32_t)__ffs((int)m) - 1u;
-                    const uint4 u2 = fetch(base, 3u + PU * c);
-                    if (__uint_as_float(u2.w) > held()) break;  // each chunk is sorted front to back
-                    test(fetch(base, 1u + PU * c), fetch(base, 2u + PU * c), u2);
-                }
-            }
-            base = hdr.y;
-        }
-#pragma unroll
-        for (int k = 0; k < GP; k++) {
-            const int s0 = g0 + 2 * k, s1 = s0 + 1;
-            if (s0 < S) {
-                put_winner(s0, bi[k][0], bd[k].x);
-                if (bi[k][0] != NO_HIT) tmin = fminf(tmin, fabsf(bd[k].x)), tmax = fmaxf(tmax, fabsf(bd[k].x));
-            }
-            if (s1 < S) {
-                put_winner(s1, bi[k][1], bd[k].y);
-                if (bi[k][1] != NO_HIT) tmin = fminf(tmin, fabsf(bd[k].y)), tmax = fmaxf(tmax, fabsf(bd[k].y));
-            }
-        }
-    }
-}
-
-// Issue the asynchronous copy of a chain's first chunk (at most POL::STAGED candidates of REC units each) into `stage`.
-template <class POL, uint32_t REC>
-RT_DEV void stage_chunk(const RenderParams &p, uint4 *stage, const uint32_t head) {
-    const uint32_t n = min(POL::ld(&p.pool[head]).x, POL::STAGED);
-    const uint32_t units = 1u + REC * n;
-    for (uint32_t u = POL::tid(); u < units; u += POL::nthreads()) stage_async(&stage[u], &p.pool[head + u]);
-}
-
-template <int SPP, int PXW, int PXH, int CW, int CH>
-__global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phase_test_primary(const RenderParams p) {
-    using G = Geo<SPP, PXW, PXH, CW, CH>;
-    __shared__ uint4 stage[1 + PU * T_CAND];  // the cull tile's first candidate chunk, shared by its pixel tiles
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const G geo(p.width, p.row_count);
-    // one block per cull tile, one warp per pixel tile of it
-    const uint32_t ct = blockIdx.y * geo.ctiles_x + blockIdx.x;  // 2-D grid of cull tiles: no division
-    const uint32_t pt_x = blockIdx.x * CW + (uint32_t)(warp % CW), pt_y = blockIdx.y * CH + (uint32_t)(warp / CW);
-    const uint32_t pt = pt_y * geo.ptiles_x + pt_x;
-    const uint32_t head = p.tile_hdr[ct].x;
-    if (head == NO_CHUNK) return;  // no candidate at all: K4 sees an empty hit range and never reads the winners
-    const bool staged = head != OVERFLOWED;
-    if (staged) stage_chunk<BlockPol, PU>(p, stage, head);  // asynchronous: awaited inside test_tile
-    if (pt_x >= geo.ptiles_x || pt_y >= geo.ptiles_y) {  // cull tile on the frame edge: only the block's barrier is left to do
-        if (staged) {
+        // One pass covers all of the lane's slots (S <= 4): the staged chunk is awaited after ray generation, so
+        // the copy overlaps it.  With more passes the deferred barrier costs registers (spills under the 64-register
+        // cap), so it is taken up front.
+        constexpr bool LAZY = S <= 4;
+        uint32_t mask0 = 0;  // mask of the first 32 candidates of the first chunk: reused by every slot pair
+        if (!LAZY) {
             stage_wait();
             __syncthreads();
+            mask0 = chunk_mask(head, 0u, min(stage[0].x, 32u));
         }
-        return;
+        // GP packed pairs (two slots each) per pass: every candidate record is loaded once for all of them and
+        // the pairs' dependency chains interleave.
+        constexpr int GP = (S >= 4) ? 2 : 1;
+#pragma unroll 1
+        for (int g0 = 0; g0 < S; g0 += 2 * GP) {
+            V3x2 d[GP];
+            F2 bd[GP];
+            uint32_t bi[GP][2];
+#pragma unroll
+            for (int k = 0; k < GP; k++) {
+                const int s0 = min(g0 + 2 * k, S - 1), s1 = min(s0 + 1, S - 1);  // a pair past the end repeats the last slot
+                uint32_t x0, j0, x1, j1;
+                slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s0 / NS, x0, j0);
+                slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s1 / NS, x1, j1);
+                d[k] = slot_dir2<SPP>(one, p, x0, image_row(p, j0), s0 % NS, x1, image_row(p, j1), s1 % NS);
+                bd[k] = f2s(RT_INF);
+                bi[k][0] = bi[k][1] = NO_HIT;
+            }
+            if (LAZY) {  // the only pass: every warp of the block arrives here exactly once
+                stage_wait();
+                __syncthreads();
+                mask0 = chunk_mask(head, 0u, min(stage[0].x, 32u));
+            }
+            auto test = [&](const uint4 u0, const uint4 u1, const uint4 u2) {
+                V3x2 v;
+                v.x = f2(__uint_as_float(u0.x), __uint_as_float(u0.y));
+                v.y = f2(__uint_as_float(u0.z), __uint_as_float(u0.w));
+                v.z = f2(__uint_as_float(u1.x), __uint_as_float(u1.y));
+                const F2 nvv = f2(__uint_as_float(u1.z), __uint_as_float(u1.w));
+                const F2 rr = f2(__uint_as_float(u2.x), __uint_as_float(u2.y));
+                const uint32_t idx = u2.z;
+#pragma unroll
+                for (int k = 0; k < GP; k++) {
+                    const F2 dist = primary_distance2(one, v, nvv, rr, d[k]);
+                    // primitive.rs:79 + pre-order visiting: strictly closer wins, ties -> lowest index
+                    if (dist.x < bd[k].x || (dist.x == bd[k].x && idx < bi[k][0] && bi[k][0] != NO_HIT)) bd[k].x = dist.x, bi[k][0] = idx;
+                    if (dist.y < bd[k].y || (dist.y == bd[k].y && idx < bi[k][1] && bi[k][1] != NO_HIT)) bd[k].y = dist.y, bi[k][1] = idx;
+                }
+            };
+            // farthest distance the lane still has to beat (+inf while one of its slots has no hit)
+            auto held = [&]() {
+                float h = fmaxf(bd[0].x, bd[0].y);
+#pragma unroll
+                for (int k = 1; k < GP; k++) h = fmaxf(h, fmaxf(bd[k].x, bd[k].y));
+                return h;
+            };
+            // hot path: the first 32 candidates of the staged chunk, straight from shared memory; they come
+            // front to back, so the lane is done once a candidate cannot start before what it holds
+            for (uint32_t m = mask0; m; m &= m - 1u) {
+                const uint32_t c = (uint32_t)__ffs((int)m) - 1u;
+                const uint4 u2 = stage[3u + PU * c];
+                if (__uint_as_float(u2.w) > held()) break;
+                test(stage[1u + PU * c], stage[2u + PU * c], u2);
+            }
+            // cold path: the rest of the staged chunk and any further chunks of the chain
+            for (uint32_t base = head; base != NO_CHUNK;) {
+                const uint4 hdr = fetch(base, 0u);
+                const uint32_t n = hdr.x;
+                for (uint32_t c0 = (base == head) ? 32u : 0u; c0 < n; c0 += 32) {
+                    for (uint32_t m = chunk_mask(base, c0, min(n, c0 + 32u)); m; m &= m - 1u) {
+                        const uint32_t c = c0 + (uint32_t)__ffs((int)m) - 1u;
+                        const uint4 u2 = fetch(base, 3u + PU * c);
+                        if (__uint_as_float(u2.w) > held()) break;  // each chunk is sorted front to back
+                        test(fetch(base, 1u + PU * c), fetch(base, 2u + PU * c), u2);
+                    }
+                }
+                base = hdr.y;
+            }
+#pragma unroll
+            for (int k = 0; k < GP; k++) {
+                const int s0 = g0 + 2 * k, s1 = s0 + 1;
+                if (s0 < S) {
+                    put_winner(s0, bi[k][0], bd[k].x);
+                    if (bi[k][0] != NO_HIT) tmin = fminf(tmin, fabsf(bd[k].x)), tmax = fmaxf(tmax, fabsf(bd[k].x));
+                }
+                if (s1 < S) {
+                    put_winner(s1, bi[k][1], bd[k].y);
+                    if (bi[k][1] != NO_HIT) tmin = fminf(tmin, fabsf(bd[k].y)), tmax = fmaxf(tmax, fabsf(bd[k].y));
+                }
+            }
+        }
     }
-    float tmin = RT_INF, tmax = 0.0f;
-    test_tile<G, BlockPol>(p, stage, head, pt_x, pt_y, p.winner + (size_t)pt * G::WINNER_WORDS, lane, tmin, tmax);
     // hit-distance range of the cull tile (positive floats order as uints)
     const uint32_t lo = __reduce_min_sync(FULLMASK, __float_as_uint(tmin));
     const uint32_t hi = __reduce_max_sync(FULLMASK, __float_as_uint(tmax));
@@ -529,41 +461,50 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
 // ---------------------------------------------------------------------------
 // K3: shadow cull, one warp per cull tile
 // ---------------------------------------------------------------------------
-// Beam of the shadow rays a cull tile can cast: their origins lie within rho of the tile's view axis between
-// the nearest (tlo) and the farthest (thi) hit distance of its samples; swept along -light.
-RT_DEV ShadowBeam make_shadow_beam(const RenderParams &p, const PrimaryBeam &pb, const float tlo, const float thi) {
+template <int SPP, int PXW, int PXH, int CW, int CH>
+__global__ void __launch_bounds__(32 * P_WARPS) phase_cull_shadow(const RenderParams p) {
+    using G = Geo<SPP, PXW, PXH, CW, CH>;
+    __shared__ CullShared shared[P_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const G geo(p.width, p.row_count);
+    const uint32_t ct = blockIdx.x * P_WARPS + warp;
+    if (ct >= geo.n_ctiles()) return;
+    CullShared &sm = shared[warp];
+    const uint4 hdr = p.tile_hdr[ct];
+    if (hdr.z == 0x7f800000u || hdr.x == OVERFLOWED) {  // no hit in this tile / tile handled by the per-lane walk
+        if (lane == 0) reinterpret_cast<uint32_t *>(&p.tile_hdr[ct])[1] = hdr.x == OVERFLOWED ? OVERFLOWED : NO_CHUNK;
+        return;
+    }
+    const PrimaryBeam pb = cull_tile_beam<G>(p, ct % geo.ctiles_x, ct / geo.ctiles_x);
     const V3 eye = v3(p.eye[0], p.eye[1], p.eye[2]);
     ShadowBeam sb;
-    const float off = thi * 3.6e-4f + 1e-6f;  // |normal * distance * sqrt(eps)| <= distance * 3.4527e-4
-    float a0 = adiv(tlo, pb.secp) * 0.99999f - off;
-    float a1 = thi + off;
-    if (pb.wide) {  // no usable cone: origins anywhere within thi of the eye
-        a0 = 0.0f;
-        a1 = 0.0f;
-        sb.rho = thi * 1.001f + off;
-    } else {
-        sb.rho = thi * (pb.tanp + 3.6e-4f) * 1.001f + 1e-6f;
+    {
+        const float tlo = __uint_as_float(hdr.z), thi = __uint_as_float(hdr.w);
+        const float off = thi * 3.6e-4f + 1e-6f;  // |normal * distance * sqrt(eps)| <= distance * 3.4527e-4
+        float a0 = adiv(tlo, pb.secp) * 0.99999f - off;
+        float a1 = thi + off;
+        if (pb.wide) {  // no usable cone: origins anywhere within thi of the eye
+            a0 = 0.0f;
+            a1 = 0.0f;
+            sb.rho = thi * 1.001f + off;
+        } else {
+            sb.rho = thi * (pb.tanp + 3.6e-4f) * 1.001f + 1e-6f;
+        }
+        sb.none = false;
+        sb.px = fmaf(a0, pb.ax, eye.x), sb.py = fmaf(a0, pb.ay, eye.y), sb.pz = fmaf(a0, pb.az, eye.z);
+        sb.ax = pb.ax, sb.ay = pb.ay, sb.az = pb.az;
+        sb.lx = -p.light[0], sb.ly = -p.light[1], sb.lz = -p.light[2];  // render.rs:206
+        sb.len = a1 - a0;
+        float nx = sb.ay * sb.lz - sb.az * sb.ly, ny = sb.az * sb.lx - sb.ax * sb.lz, nz = sb.ax * sb.ly - sb.ay * sb.lx;
+        float sn = asqrt(nx * nx + ny * ny + nz * nz);
+        sb.degenerate = pb.wide || !(sn > 0.05f);
+        float isn = adiv(1.0f, fmaxf(sn, 1e-20f));
+        sb.nx = nx * isn, sb.ny = ny * isn, sb.nz = nz * isn;
+        sb.cosq = sb.ax * sb.lx + sb.ay * sb.ly + sb.az * sb.lz;
+        sb.inv_sin = isn * 1.00001f;
+        sb.inv_sin2 = isn * isn * 1.00001f;
+        sb.rmin = p.leaf_rmin;
     }
-    sb.none = false;
-    sb.px = fmaf(a0, pb.ax, eye.x), sb.py = fmaf(a0, pb.ay, eye.y), sb.pz = fmaf(a0, pb.az, eye.z);
-    sb.ax = pb.ax, sb.ay = pb.ay, sb.az = pb.az;
-    sb.lx = -p.light[0], sb.ly = -p.light[1], sb.lz = -p.light[2];  // render.rs:206
-    sb.len = a1 - a0;
-    float nx = sb.ay * sb.lz - sb.az * sb.ly, ny = sb.az * sb.lx - sb.ax * sb.lz, nz = sb.ax * sb.ly - sb.ay * sb.lx;
-    float sn = asqrt(nx * nx + ny * ny + nz * nz);
-    sb.degenerate = pb.wide || !(sn > 0.05f);
-    float isn = adiv(1.0f, fmaxf(sn, 1e-20f));
-    sb.nx = nx * isn, sb.ny = ny * isn, sb.nz = nz * isn;
-    sb.cosq = sb.ax * sb.lx + sb.ay * sb.ly + sb.az * sb.lz;
-    sb.inv_sin = isn * 1.00001f;
-    sb.inv_sin2 = isn * isn * 1.00001f;
-    sb.rmin = p.leaf_rmin;
-    return sb;
-}
-
-// Walk the hierarchy for the shadow rays of one cull tile and append the candidates as a chain; returns its
-// head (NO_CHUNK: nothing can occlude; OVERFLOWED: the tile's shadow rays take the per-lane any-hit walk).
-RT_DEV uint32_t cull_shadow_tile(const RenderParams &p, CullShared &sm, const ShadowBeam &sb, const int lane, PrivPool *priv) {
     CullState cs;
     cull_begin<false>(p, sm, sb, lane, cs);
     uint32_t head = NO_CHUNK;
@@ -575,46 +516,29 @@ RT_DEV uint32_t cull_shadow_tile(const RenderParams &p, CullShared &sm, const Sh
         // Past a few hundred candidates the list costs more than the per-lane any-hit walk (measured at level 10:
         // tiles with 1,000-2,800 candidates); such a tile is handed to that walk, as on pool exhaustion.
         if (total > (uint32_t)RT_SHADOW_CAP) head = OVERFLOWED;
-        head = flush_shadow(p, sm, sb, lane, cs.ncand, head, priv);
+        head = flush_shadow(p, sm, sb, lane, cs.ncand, head);
         __syncwarp();
     } while (!done && head != OVERFLOWED);
-    return head;
-}
-
-template <int SPP, int PXW, int PXH, int CW, int CH>
-__global__ void __launch_bounds__(32 * P_WARPS) phase_cull_shadow(const RenderParams p) {
-    using G = Geo<SPP, PXW, PXH, CW, CH>;
-    __shared__ CullShared shared[P_WARPS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const G geo(p.width, p.row_count);
-    const uint32_t ct = blockIdx.x * P_WARPS + warp;
-    if (ct >= geo.n_ctiles()) return;
-    const uint4 hdr = p.tile_hdr[ct];
-    if (hdr.z == 0x7f800000u || hdr.x == OVERFLOWED) {  // no hit in this tile / tile handled by the per-lane walk
-        if (lane == 0) reinterpret_cast<uint32_t *>(&p.tile_hdr[ct])[1] = hdr.x == OVERFLOWED ? OVERFLOWED : NO_CHUNK;
-        return;
-    }
-    const PrimaryBeam pb = cull_tile_beam<G>(p, ct % geo.ctiles_x, ct / geo.ctiles_x);
-    const ShadowBeam sb = make_shadow_beam(p, pb, __uint_as_float(hdr.z), __uint_as_float(hdr.w));
-    const uint32_t head = cull_shadow_tile(p, shared[warp], sb, lane, nullptr);
     if (lane == 0) reinterpret_cast<uint32_t *>(&p.tile_hdr[ct])[1] = head;
 }
 
 // ---------------------------------------------------------------------------
 // K4: shading, shadow tests, accumulation, store; one warp per pixel tile
 // ---------------------------------------------------------------------------
-// Pixel tile (pt_x, pt_y) of a cull tile whose header is tile_hdr = {primary chain, shadow chain, tmin, tmax}:
-// reads the winners test_tile stored, shades, tests the shadow rays against the shadow chain (its first
-// POL::STAGED candidates staged in `stage`; in the one-group case the copy may still be in flight and is
-// awaited here), accumulates in reference order and stores the pixels.
-template <class G, class POL, bool DIAG>
-RT_DEV void shade_tile(const RenderParams &p, const uint4 *stage, const uint4 tile_hdr, const uint32_t pt_x, const uint32_t pt_y,
-                       const uint32_t *winner, const int lane, unsigned &n_hits_out, unsigned &n_shadow_out) {
-    constexpr int SPP = G::SPP_, PXW = G::PXW_, PXH = G::PXH_;
+template <int SPP, int PXW, int PXH, int CW, int CH, bool DIAG>
+__global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phase_shade_store(const RenderParams p) {
+    using G = Geo<SPP, PXW, PXH, CW, CH>;
     constexpr int S = G::S, NS = G::NS;
-    unsigned n_hits = 0, n_shadow = 0;
+    __shared__ uint4 stage[1 + SU * T_CAND];  // the cull tile's first shadow-candidate chunk
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const G geo(p.width, p.row_count);
+    // one block per cull tile, one warp per pixel tile of it
+    const uint32_t ct = blockIdx.y * geo.ctiles_x + blockIdx.x;  // 2-D grid of cull tiles: no division
+    const uint32_t pt_x = blockIdx.x * CW + (uint32_t)(warp % CW), pt_y = blockIdx.y * CH + (uint32_t)(warp / CW);
+    const uint32_t pt = pt_y * geo.ptiles_x + pt_x;
     const uint32_t tile_x0 = pt_x * G::TW, tile_j0 = pt_y * G::TH;
-    constexpr bool WDIST = G::WDIST;  // K2 stored the winner's distance next to its index
+    constexpr bool WDIST = NS == 1;  // K2 stored the winner's distance next to its index
+    const uint32_t *winner = p.winner + (size_t)pt * S * 32 * (WDIST ? 2 : 1);
     const ONE2 one = f2s(p.one);  // 1.0f the compiler cannot see (rt_pack.cuh)
 
     const V3 eye = v3(p.eye[0], p.eye[1], p.eye[2]);
@@ -630,20 +554,29 @@ RT_DEV void shade_tile(const RenderParams &p, const uint4 *stage, const uint4 ti
     uint32_t bx, bj;
     slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, 0, bx, bj);
     const bool lane_in = bx < p.width && bj < p.row_count;
+    const uint4 tile_hdr = p.tile_hdr[ct];
     const uint32_t head = tile_hdr.y;
-    constexpr bool LAZY = S <= 4;  // one group per lane: await the staged chunk after phase A (see test_tile)
+    constexpr bool LAZY = S <= 4;  // one group per lane: await the staged chunk after phase A (see K2)
     const bool staged = head < OVERFLOWED;
-    if (!LAZY && staged) {
-        stage_wait();
-        POL::sync();
+    if (staged) {  // stage the first chunk (almost always the only one) in shared memory, asynchronously
+        const uint32_t units = 1u + SU * __ldg(&p.pool[head]).x;
+        for (uint32_t u = threadIdx.x; u < units; u += blockDim.x) {
+            if (LAZY) stage_async(&stage[u], &p.pool[head + u]);
+            else stage[u] = __ldg(&p.pool[head + u]);
+        }
     }
+    if (!LAZY) __syncthreads();
+    if (pt_x >= geo.ptiles_x || pt_y >= geo.ptiles_y) {  // cull tile on the frame edge: only the block's barrier is left to do
+        if (LAZY && staged) {
+            stage_wait();
+            __syncthreads();
+        }
+        return;
+    }
+    unsigned n_hits = 0, n_shadow = 0;
     float cr = 0.0f, cg = 0.0f, alpha = 0.0f;  // red, green (= blue), alpha of the pixel being accumulated (render.rs:233-234)
     if (tile_hdr.z == 0x7f800000u) {
         // no ray of this cull tile hit anything: every sample adds BACKGROUND (render.rs:190-193)
-        if (LAZY && staged) {  // keep the barrier count of the other branch (never taken: no hit means no shadow chain)
-            stage_wait();
-            POL::sync();
-        }
         if (lane_in) {
             for (int smp = 0; smp < NS; smp++) cr = fadd(cr, BG_R), cg = fadd(cg, BG_G);
             const uint32_t g8 = scale_u8_fast(fmul(cg, recip));
@@ -717,9 +650,9 @@ RT_DEV void shade_tile(const RenderParams &p, const uint4 *stage, const uint4 ti
                     xs[2 * k] = xs[2 * k + 1] = js[2 * k] = js[2 * k + 1] = 0xffffffffu;
                 }
             }
-            if (LAZY && staged) {  // the only group: every thread sharing the stage arrives here exactly once per tile
+            if (LAZY && staged) {  // the only group: every warp of the block arrives here exactly once
                 stage_wait();
-                POL::sync();
+                __syncthreads();
             }
             // ---- B: shadow rays {pos: o, dir: -light} against the tile's candidates (render.rs:202-208) ----
             if (head == OVERFLOWED) {  // per-lane walk, any-hit
@@ -767,15 +700,12 @@ RT_DEV void shade_tile(const RenderParams &p, const uint4 *stage, const uint4 ti
                     }
                 }
                 ulo = warp_min_f(ulo), uhi = warp_max_f(uhi), vlo = warp_min_f(vlo), vhi = warp_max_f(vhi);
-                // one chunk of the tile's chain: STAGED = the first one, read from shared memory (its first POL::STAGED
-                // candidates; the FUSED variant stages fewer than a chunk can hold and reads the rest like any other chunk)
-                auto run_chunk = [&](auto staged_tag, uint32_t base, uint32_t c_begin) -> uint32_t {
+                // one chunk of the tile's chain: STAGED = the first one, read from shared memory
+                auto run_chunk = [&](auto staged_tag, uint32_t base) -> uint32_t {
                     constexpr bool STAGED = decltype(staged_tag)::value;
-                    auto unit = [&](uint32_t off) { return STAGED ? stage[off] : POL::ld(&p.pool[base + off]); };
-                    uint4 hdr = unit(0u);
-                    const uint32_t next = hdr.y;
-                    if (STAGED && POL::STAGED < (uint32_t)T_CAND) hdr.x = min(hdr.x, POL::STAGED);
-                    for (uint32_t c0 = c_begin; c0 < hdr.x; c0 += 32) {
+                    auto unit = [&](uint32_t off) { return STAGED ? stage[off] : __ldg(&p.pool[base + off]); };
+                    const uint4 hdr = unit(0u);
+                    for (uint32_t c0 = 0; c0 < hdr.x; c0 += 32) {
                         // warp level: lane tests candidate c0 + lane (disc vs rectangle)
                         bool w_ok = false;
                         if (c0 + lane < hdr.x) {
@@ -810,13 +740,10 @@ RT_DEV void shade_tile(const RenderParams &p, const uint4 *stage, const uint4 ti
                             shadow_test(1, u0, u1);
                         }
                     }
-                    return next;
+                    return hdr.y;
                 };
-                uint32_t next = run_chunk(std::true_type{}, head, 0u);
-                if constexpr (POL::STAGED < (uint32_t)T_CAND) {  // the unstaged rest of the first chunk (a chunk holds <= T_CAND)
-                    if (stage[0].x > POL::STAGED) run_chunk(std::false_type{}, head, POL::STAGED);
-                }
-                while (next != NO_CHUNK && __ballot_sync(FULLMASK, pend != 0u) != 0u) next = run_chunk(std::false_type{}, next, 0u);
+                uint32_t next = run_chunk(std::true_type{}, head);
+                while (next != NO_CHUNK && __ballot_sync(FULLMASK, pend != 0u) != 0u) next = run_chunk(std::false_type{}, next);
             }
             // ---- C: accumulate in reference sample order (render.rs:236-250), quantise, store (render.rs:92-109) ----
             // Only red and green are carried: OBJECT, BACKGROUND and AMBIENT_OFFSET have g == b (render.rs:172-186)
@@ -884,133 +811,14 @@ RT_DEV void shade_tile(const RenderParams &p, const uint4 *stage, const uint4 ti
             }
         }
     }
-    if (DIAG) n_hits_out += n_hits, n_shadow_out += n_shadow;
-}
-
-// DIAG: per-warp totals of primary hits and shadow rays into the frame's counters.
-RT_DEV void add_ray_counters(const RenderParams &p, const int lane, unsigned n_hits, unsigned n_shadow) {
-    if (!p.ray_counters) return;
-    n_hits = __reduce_add_sync(FULLMASK, n_hits);
-    n_shadow = __reduce_add_sync(FULLMASK, n_shadow);
-    if (lane == 0) {
-        atomicAdd(&p.ray_counters[0], (unsigned long long)n_hits);
-        atomicAdd(&p.ray_counters[1], (unsigned long long)n_shadow);
+    if (DIAG && p.ray_counters) {
+        n_hits = __reduce_add_sync(FULLMASK, n_hits);
+        n_shadow = __reduce_add_sync(FULLMASK, n_shadow);
+        if (lane == 0) {
+            atomicAdd(&p.ray_counters[0], (unsigned long long)n_hits);
+            atomicAdd(&p.ray_counters[1], (unsigned long long)n_shadow);
+        }
     }
-}
-
-template <int SPP, int PXW, int PXH, int CW, int CH, bool DIAG>
-__global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phase_shade_store(const RenderParams p) {
-    using G = Geo<SPP, PXW, PXH, CW, CH>;
-    __shared__ uint4 stage[1 + SU * T_CAND];  // the cull tile's first shadow-candidate chunk
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const G geo(p.width, p.row_count);
-    // one block per cull tile, one warp per pixel tile of it
-    const uint32_t ct = blockIdx.y * geo.ctiles_x + blockIdx.x;  // 2-D grid of cull tiles: no division
-    const uint32_t pt_x = blockIdx.x * CW + (uint32_t)(warp % CW), pt_y = blockIdx.y * CH + (uint32_t)(warp / CW);
-    const uint32_t pt = pt_y * geo.ptiles_x + pt_x;
-    const uint4 tile_hdr = p.tile_hdr[ct];
-    const bool staged = tile_hdr.y < OVERFLOWED;
-    if (staged) stage_chunk<BlockPol, SU>(p, stage, tile_hdr.y);  // asynchronous: awaited inside shade_tile
-    if (pt_x >= geo.ptiles_x || pt_y >= geo.ptiles_y) {  // cull tile on the frame edge: only the block's barrier is left to do
-        if (staged) {
-            stage_wait();
-            __syncthreads();
-        }
-        return;
-    }
-    unsigned n_hits = 0, n_shadow = 0;
-    shade_tile<G, BlockPol, DIAG>(p, stage, tile_hdr, pt_x, pt_y, p.winner + (size_t)pt * G::WINNER_WORDS, lane, n_hits, n_shadow);
-    if (DIAG) add_ray_counters(p, lane, n_hits, n_shadow);
-}
-
-
-// ---------------------------------------------------------------------------
-// FUSED: one persistent warp per cull tile, all four phases back to back
-// ---------------------------------------------------------------------------
-static constexpr int F_WARPS = 4;  // independent warps per block (they share nothing but the block's resources)
-#ifndef RT_FUSED_POOL_UNITS
-#define RT_FUSED_POOL_UNITS 2048  // 16-byte units of private candidate pool per warp (512 primary records)
-#endif
-
-union FusedShared {
-    CullShared cull;                      // phases 1 and 3: stack + candidate list of the walk
-    uint4 stage[1 + PU * WarpPol::STAGED];  // phases 2 and 4: the first chunk of the chain being consumed
-};
-
-template <int SPP, int PXW, int PXH, int CW, int CH, bool DIAG>
-__global__ void __launch_bounds__(32 * F_WARPS, phased_min_blocks(F_WARPS)) fused_tile_kernel(const RenderParams p) {
-    using G = Geo<SPP, PXW, PXH, CW, CH>;
-    __shared__ FusedShared shared[F_WARPS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t gwarp = blockIdx.x * F_WARPS + (uint32_t)warp;
-    FusedShared &sm = shared[warp];
-    const G geo(p.width, p.row_count);
-    const uint32_t n_ct = geo.n_ctiles();
-    // this warp's scratch: winners of one cull tile's pixel tiles, and its slice of the candidate pool
-    uint32_t *const winners = p.winner + (size_t)gwarp * (CW * CH) * G::WINNER_WORDS;
-    PrivPool priv;
-    priv.base = gwarp * p.pool_cap;  // pool_cap: units per warp in this variant
-    priv.cap = p.pool_cap;
-    unsigned n_hits = 0, n_shadow = 0;
-    for (;;) {
-        uint32_t ct = 0;
-        if (lane == 0) ct = atomicAdd(p.pool_count, 1u);  // the frame's tile counter (zeroed before the launch)
-        ct = __shfl_sync(FULLMASK, ct, 0);
-        if (ct >= n_ct) break;
-        const uint32_t ct_x = ct % geo.ctiles_x, ct_y = ct / geo.ctiles_x;
-        // ---- 1: primary cull ----
-        priv.used = 0;
-        uint32_t head = NO_CHUNK;
-        {
-            const PrimaryBeam pb = cull_tile_beam<G>(p, ct_x, ct_y);
-            CullState cs;
-            cull_begin<true>(p, sm.cull, pb, lane, cs);
-            bool done;
-            do {
-                done = cull_run<true>(p, sm.cull, pb, lane, cs);
-                head = flush_primary(p, sm.cull, lane, cs.ncand, head, &priv);
-                __syncwarp();
-            } while (!done && head != OVERFLOWED);
-        }
-        // ---- 2: exact closest-hit tests of the tile's pixel tiles ----
-        uint32_t tlo = 0x7f800000u, thi = 0u;  // hit-distance range of the cull tile (positive floats order as uints)
-        if (head != NO_CHUNK) {
-            if (head != OVERFLOWED) stage_chunk<WarpPol, PU>(p, sm.stage, head);  // awaited inside test_tile
-            float tmin = RT_INF, tmax = 0.0f;
-#pragma unroll 1
-            for (int t = 0; t < CW * CH; t++) {
-                const uint32_t pt_x = ct_x * CW + (uint32_t)(t % CW), pt_y = ct_y * CH + (uint32_t)(t / CW);
-                if (pt_x < geo.ptiles_x && pt_y < geo.ptiles_y)
-                    test_tile<G, WarpPol>(p, sm.stage, head, pt_x, pt_y, winners + (size_t)t * G::WINNER_WORDS, lane, tmin, tmax);
-            }
-            tlo = __reduce_min_sync(FULLMASK, __float_as_uint(tmin));
-            thi = __reduce_max_sync(FULLMASK, __float_as_uint(tmax));
-            stage_wait();  // a tile whose pixel tiles all lie outside the frame never awaited its copy
-            __syncwarp();  // every lane is done with the staged chunk: the walk below reuses the memory
-        }
-        // ---- 3: shadow cull ----
-        uint32_t shead = NO_CHUNK;
-        if (head == OVERFLOWED) {
-            shead = OVERFLOWED;
-        } else if (tlo != 0x7f800000u) {
-            priv.used = 0;  // the primary chain is dead: its units are reused
-            const PrimaryBeam pb = cull_tile_beam<G>(p, ct_x, ct_y);  // again: cheaper than keeping it live across phase 2
-            const ShadowBeam sb = make_shadow_beam(p, pb, __uint_as_float(tlo), __uint_as_float(thi));
-            shead = cull_shadow_tile(p, sm.cull, sb, lane, &priv);
-        }
-        // ---- 4: shading, shadow tests, store ----
-        const uint4 tile_hdr = make_uint4(head, shead, tlo, thi);
-        if (shead < OVERFLOWED) stage_chunk<WarpPol, SU>(p, sm.stage, shead);  // awaited inside shade_tile
-#pragma unroll 1
-        for (int t = 0; t < CW * CH; t++) {
-            const uint32_t pt_x = ct_x * CW + (uint32_t)(t % CW), pt_y = ct_y * CH + (uint32_t)(t / CW);
-            if (pt_x < geo.ptiles_x && pt_y < geo.ptiles_y)
-                shade_tile<G, WarpPol, DIAG>(p, sm.stage, tile_hdr, pt_x, pt_y, winners + (size_t)t * G::WINNER_WORDS, lane, n_hits, n_shadow);
-        }
-        stage_wait();
-        __syncwarp();  // before the next tile's walk overwrites the stage
-    }
-    if (DIAG) add_ray_counters(p, lane, n_hits, n_shadow);
 }
 
 }  // namespace rt
@@ -1040,51 +848,6 @@ static cudaError_t launch_phased(bool diag, const RenderParams &p, cudaStream_t 
     else
         phase_shade_store<SPP, PXW, PXH, CW, CH, false><<<tiles2d, 32 * CW * CH, 0, stream>>>(p);
     return cudaGetLastError();
-}
-
-// FUSED: grid = SMs x resident blocks (occupancy query), persistent warps.
-template <int SPP, int PXW, int PXH, int CW, int CH>
-static cudaError_t launch_fused(bool diag, const RenderParams &p, cudaStream_t stream, uint32_t blocks) {
-    using G = Geo<SPP, PXW, PXH, CW, CH>;
-    const G geo(p.width, p.row_count);
-    if (geo.n_ctiles() == 0) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(p.pool_count, 0, sizeof(uint32_t), stream);
-    if (e != cudaSuccess) return e;
-    const uint32_t need = (geo.n_ctiles() + F_WARPS - 1) / F_WARPS;
-    const uint32_t grid = blocks < need ? blocks : need;
-    if (diag)
-        fused_tile_kernel<SPP, PXW, PXH, CW, CH, true><<<grid, 32 * F_WARPS, 0, stream>>>(p);
-    else
-        fused_tile_kernel<SPP, PXW, PXH, CW, CH, false><<<grid, 32 * F_WARPS, 0, stream>>>(p);
-    return cudaGetLastError();
-}
-
-// Persistent grid of the FUSED variant on the current device and the scratch it needs: per warp, the winners of
-// one cull tile's pixel tiles and RT_FUSED_POOL_UNITS units of candidate pool.
-void rt_fused_scratch(uint32_t spp, uint32_t *blocks, size_t *winner_bytes, uint32_t *pool_units_per_warp) {
-    int dev = 0, sms = 148, per_sm = phased_min_blocks(F_WARPS);
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    uint32_t words = 0;
-    switch (spp) {
-        case 1: words = 4 * Geo<1, 2, 2, 2, 2>::WINNER_WORDS; break;
-        case 2: words = 4 * Geo<2, 1, 1, 2, 2>::WINNER_WORDS; break;
-        case 3: words = 4 * Geo<3, 1, 1, 2, 2>::WINNER_WORDS; break;
-        default: words = 4 * Geo<4, 1, 1, 2, 2>::WINNER_WORDS; break;
-    }
-    *blocks = (uint32_t)(sms * per_sm);
-    *winner_bytes = (size_t)*blocks * F_WARPS * words * sizeof(uint32_t);
-    *pool_units_per_warp = RT_FUSED_POOL_UNITS;
-}
-
-cudaError_t rt_launch_render_fused(bool diag, const RenderParams &p, cudaStream_t stream, uint32_t blocks) {
-    switch (p.spp) {
-        case 1: return launch_fused<1, 2, 2, 2, 2>(diag, p, stream, blocks);
-        case 2: return launch_fused<2, 1, 1, 2, 2>(diag, p, stream, blocks);
-        case 3: return launch_fused<3, 1, 1, 2, 2>(diag, p, stream, blocks);
-        case 4: return launch_fused<4, 1, 1, 2, 2>(diag, p, stream, blocks);
-        default: return cudaErrorInvalidValue;
-    }
 }
 
 // Scratch the phased pipeline needs for a frame of `rows` x `width`, `spp`: winner

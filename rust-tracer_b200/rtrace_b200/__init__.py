@@ -15,7 +15,7 @@ PKG_DIR = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("RTRACE_B200_LIB") or os.path.join(PKG_DIR, "librtrace_b200.so")  # env: kernel experiments
 
 RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_NOMEM, RT_ERR_BUFFER = 0, -1, -2, -3, -4
-VARIANT_AUTO, VARIANT_LANE, VARIANT_WARP, VARIANT_TILE, VARIANT_PHASED, VARIANT_FUSED = 0, 1, 2, 3, 4, 5
+VARIANT_AUTO, VARIANT_LANE, VARIANT_WARP, VARIANT_TILE, VARIANT_PHASED = 0, 1, 2, 3, 4
 
 # every symbol include/rtrace.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [

@@ -57,7 +57,7 @@ def test_multi_gpu_full_size_frames_match_oracle_hash(rt, replicas, w, h, spp, l
     scenes = replicas(level)
     img, st = rt.Renderer.render_multi(rt.RenderOptions(w, h, spp), scenes, want_stats=True)
     assert hashlib.sha256(img.tobytes()).hexdigest() == case["rgba_sha256"]
-    assert st.gpus == len(scenes) and st.variant_used in (rt.VARIANT_PHASED, rt.VARIANT_FUSED)
+    assert st.gpus == len(scenes) and st.variant_used == rt.VARIANT_PHASED
 
 
 def test_same_scene_twice_is_rejected(rt, gpu_scene8):

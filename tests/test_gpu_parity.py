@@ -20,7 +20,7 @@ DERIVED = json.load(open(os.path.join(HERE, "golden", "oracle_derived.json")))
 
 
 def variants(rt):
-    return [rt.VARIANT_LANE, rt.VARIANT_WARP, rt.VARIANT_TILE, rt.VARIANT_PHASED, rt.VARIANT_FUSED]
+    return [rt.VARIANT_LANE, rt.VARIANT_WARP, rt.VARIANT_TILE, rt.VARIANT_PHASED]
 
 
 def assert_same(gpu, ref, what=""):
@@ -80,15 +80,9 @@ def test_baseline_frames_match_oracle_fixture(rt, case):
     C2 (3840x2160, 1 spp) at levels 8/9/10, C3 (3840x2160, 4x4, level 9 = C5's frame 0) and C4 (7680x4320, 4x4,
     level 9) -- plus the ray counts, counted on the device the way the reference's work is counted."""
     gs = rt.Scene(level=case["level"])
-    try:
-        for v in (rt.VARIANT_AUTO, rt.VARIANT_FUSED, rt.VARIANT_PHASED):
-            rt.set_variant(v)
-            img, st = rt.Renderer.render(rt.RenderOptions(case["width"], case["height"], case["spp"]), gs, want_stats=True)
-            assert hashlib.sha256(img.tobytes()).hexdigest() == case["rgba_sha256"], "variant %d" % v
-            # a candidate-list variant ran (no silent LANE fallback)
-            assert st.variant_used in (rt.VARIANT_TILE, rt.VARIANT_PHASED, rt.VARIANT_FUSED)
-    finally:
-        rt.set_variant(rt.VARIANT_AUTO)
+    img, st = rt.Renderer.render(rt.RenderOptions(case["width"], case["height"], case["spp"]), gs, want_stats=True)
+    assert hashlib.sha256(img.tobytes()).hexdigest() == case["rgba_sha256"]
+    assert st.variant_used in (rt.VARIANT_TILE, rt.VARIANT_PHASED)   # a candidate-list variant ran (no silent LANE fallback)
     p, s = gs.count_rays(case["width"], case["height"], case["spp"])
     assert (p, s) == (case["counters"]["primary_rays"], case["counters"]["shadow_rays"])
 
@@ -272,14 +266,12 @@ def test_candidate_pool_overflow_falls_back_to_the_lane_walk(rt, oracle_scene8, 
     """A cull tile whose candidates do not fit the pool is rendered by the per-lane walk: same bytes."""
     w, h, spp = 512, 288, 1
     ref, _ = oracle_scene8.render(w, h, spp)
+    rt.set_variant(rt.VARIANT_PHASED)
     try:
-        for variant, sizes in ((rt.VARIANT_PHASED, ("64", "600", "3000")),   # nothing fits / some tiles fit / most tiles fit
-                               (rt.VARIANT_FUSED, ("4", "24", "120"))):      # the same per warp: units of ONE tile's lists
-            rt.set_variant(variant)
-            for units in sizes:
-                os.environ["RTRACE_POOL_UNITS"] = units
-                img, kinds = rt.Renderer.render_rows(rt.RenderOptions(w, h, spp), gpu_scene8, kinds=True)
-                assert_same(img, ref, "variant %d, pool of %s units" % (variant, units))
+        for units in ("64", "600", "3000"):   # nothing fits / some tiles fit / most tiles fit
+            os.environ["RTRACE_POOL_UNITS"] = units
+            img, kinds = rt.Renderer.render_rows(rt.RenderOptions(w, h, spp), gpu_scene8, kinds=True)
+            assert_same(img, ref, "pool of %s units" % units)
     finally:
         os.environ.pop("RTRACE_POOL_UNITS", None)
         rt.set_variant(rt.VARIANT_AUTO)
@@ -341,7 +333,7 @@ def test_other_scenes_at_high_resolution(rt, oracle):
     w, h, spp = 1920, 1080, 1
     ref, _ = os_.render(w, h, spp)
     try:
-        for v in (rt.VARIANT_TILE, rt.VARIANT_PHASED, rt.VARIANT_FUSED):
+        for v in (rt.VARIANT_TILE, rt.VARIANT_PHASED):
             rt.set_variant(v)
             assert_same(rt.Renderer.render(rt.RenderOptions(w, h, spp), gs), ref, "variant %d" % v)
     finally:
@@ -390,6 +382,7 @@ def test_phased_prefilters_hold_for_cameras_and_lights(rt, oracle, kw, frames):
     rotated cameras and other lights must give the oracle's bytes too."""
     w, h, level = 1280, 720, 8
     gs, os_ = rt.Scene(level=level, **kw), oracle.Scene(level=level, **kw)
+    rt.set_variant(rt.VARIANT_PHASED)
     try:
         for i, f in enumerate(frames):
             spp = 1 + (i % 2)
@@ -397,10 +390,8 @@ def test_phased_prefilters_hold_for_cameras_and_lights(rt, oracle, kw, frames):
             for k in ("eye", "right", "up", "forward"):
                 getattr(oc, k)[:] = getattr(gc, k)[:]
             ref, _ = os_.render(w, h, spp, camera=oc)
-            for v in (rt.VARIANT_PHASED, rt.VARIANT_FUSED):
-                rt.set_variant(v)
-                img = rt.Renderer.render(rt.RenderOptions(w, h, spp), gs, camera=gc)
-                assert_same(img, ref, "%s orbit frame %d spp %d variant %d" % (kw, f, spp, v))
+            img = rt.Renderer.render(rt.RenderOptions(w, h, spp), gs, camera=gc)
+            assert_same(img, ref, "%s orbit frame %d spp %d" % (kw, f, spp))
     finally:
         rt.set_variant(rt.VARIANT_AUTO)
 
@@ -418,10 +409,8 @@ def test_phased_occlusion_culling_holds_for_other_eyes(rt, oracle, kw):
     w, h, spp, level = 1600, 900, 1, 8
     gs, os_ = rt.Scene(level=level, **kw), oracle.Scene(level=level, **kw)
     ref, _ = os_.render(w, h, spp)
+    rt.set_variant(rt.VARIANT_PHASED)
     try:
-        rt.set_variant(rt.VARIANT_FUSED)
-        assert_same(rt.Renderer.render(rt.RenderOptions(w, h, spp), gs), ref, "FUSED %s" % kw)
-        rt.set_variant(rt.VARIANT_PHASED)
         assert_same(rt.Renderer.render(rt.RenderOptions(w, h, spp), gs), ref, str(kw))
         tiles = rt.debug_phased_tiles(gs)
         assert tiles.shape[1] == 2 and int(tiles[:, 0][tiles[:, 0] != 0xffffffff].sum()) > 0
@@ -442,7 +431,7 @@ def test_translated_scenes_and_the_variant_that_ran(rt, oracle, kw, expect_lane)
     level, w, h, spp = 7, 1280, 720, 1
     gs, os_ = rt.Scene(level=level, **kw), oracle.Scene(level=level, **kw)
     ref, _ = os_.render(w, h, spp)
-    for v in (rt.VARIANT_AUTO, rt.VARIANT_PHASED, rt.VARIANT_TILE, rt.VARIANT_FUSED):
+    for v in (rt.VARIANT_AUTO, rt.VARIANT_PHASED, rt.VARIANT_TILE):
         rt.set_variant(v)
         try:
             img, st = rt.Renderer.render(rt.RenderOptions(w, h, spp), gs, want_stats=True)
@@ -461,8 +450,8 @@ def test_variant_used_reports_the_fallbacks(rt, gpu_scene8):
             return rt.Renderer.render(rt.RenderOptions(w, h, spp), scene, camera=camera, want_stats=True)[1].variant_used
         finally:
             rt.set_variant(rt.VARIANT_AUTO)
-    assert used(gpu_scene8, 2560, 1440, 1) in (rt.VARIANT_PHASED, rt.VARIANT_FUSED)
-    assert used(gpu_scene8, 640, 360, 2) in (rt.VARIANT_TILE, rt.VARIANT_PHASED, rt.VARIANT_FUSED)
+    assert used(gpu_scene8, 2560, 1440, 1) in (rt.VARIANT_PHASED)
+    assert used(gpu_scene8, 640, 360, 2) in (rt.VARIANT_TILE, rt.VARIANT_PHASED)
     assert used(gpu_scene8, 64, 64, 9, rt.VARIANT_PHASED) == rt.VARIANT_LANE          # spp beyond the fast path
     assert used(gpu_scene8, 64, 64, 1, rt.VARIANT_WARP) == rt.VARIANT_WARP
     inside = rt.Scene(level=6, eye=(0.1, -0.2, -1.6))
