@@ -254,8 +254,10 @@ bool within_analysed_range(const rt::RenderParams &p) {
 
 int kernel_variant(const rt::RenderParams &p) {
     if (p.col_count) return g_variant == RT_VARIANT_WARP ? RT_KERNEL_WARP : RT_KERNEL_LANE;  // bucket-sized window
-    const bool tile_ok = rt_tile_supported(p) && (!p.has_basis || orthonormal(p.basis)) && eye_outside_root_bound(p) &&
-                         within_analysed_range(p);
+    // what the candidate-list variants need beyond their template ranges (rt_tile_supported: spp <= 4,
+    // rt_phased_supported: spp <= 8; both: regular pyramid of level <= 10)
+    const bool geometry_ok = (!p.has_basis || orthonormal(p.basis)) && eye_outside_root_bound(p) && within_analysed_range(p);
+    const bool tile_ok = rt_tile_supported(p) && geometry_ok, phased_ok = rt_phased_supported(p) && geometry_ok;
     switch (g_variant) {
         case RT_VARIANT_LANE:
             return RT_KERNEL_LANE;
@@ -264,11 +266,11 @@ int kernel_variant(const rt::RenderParams &p) {
         case RT_VARIANT_TILE:
             return tile_ok ? RT_KERNEL_TILE : RT_KERNEL_LANE;
         case RT_VARIANT_PHASED:
-            return tile_ok ? RT_KERNEL_PHASED : RT_KERNEL_LANE;
+            return phased_ok ? RT_KERNEL_PHASED : RT_KERNEL_LANE;
         default:
             break;
     }
-    if (!tile_ok) return RT_KERNEL_LANE;
+    if (!phased_ok) return RT_KERNEL_LANE;
     // AUTO (measured on B200, profiles/r01_variant_matrix.json):
     //  * when the smallest leaves project to less than ~1.5 sample spacings the exact test is
     //    rounding noise, the cull must inflate them several-fold and the per-lane
@@ -281,7 +283,7 @@ int kernel_variant(const rt::RenderParams &p) {
     const float leaf_px = p.leaf_rmin * (float)p.width / fmaxf(dist, 1e-6f) * (float)p.spp;
     if (leaf_px < 1.5f) return RT_KERNEL_LANE;
     const uint64_t pixel_tiles = (uint64_t)p.width * p.row_count / (p.spp == 1 ? 128u : 32u);  // one warp each
-    return pixel_tiles < 8000 ? RT_KERNEL_TILE : RT_KERNEL_PHASED;
+    return (pixel_tiles < 8000 && tile_ok) ? RT_KERNEL_TILE : RT_KERNEL_PHASED;
 }
 
 int tile_shape() {

@@ -19,6 +19,8 @@ cudaError_t rt_launch_fp32_peak(int mode, float *out, int blocks, int iters, cud
 
 // TILE variant (rt_tile.cu): regular pyramids, 1 <= spp <= 4, orthonormal camera basis.
 bool rt_tile_supported(const rt::RenderParams &p);
+// PHASED variant: the same, 1 <= spp <= 8.
+bool rt_phased_supported(const rt::RenderParams &p);
 // shape 0: 16 ray slots per lane (largest tiles); shape 1: 4 slots per lane (4x more, shorter tiles)
 cudaError_t rt_launch_render_tile(bool diag, const rt::RenderParams &p, cudaStream_t stream, int shape);
 cudaError_t rt_launch_math_selftest(uint32_t n, uint32_t seed, unsigned long long *d_mismatch, cudaStream_t stream);

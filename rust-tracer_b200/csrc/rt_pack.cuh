@@ -83,7 +83,10 @@ RT_DEV F2 primary_distance2(ONE2 k, V3x2 v, F2 nvv, F2 rr, V3x2 d) {
 template <int SPP>
 RT_DEV V3x2 slot_dir2(ONE2 k, const RenderParams &p, uint32_t x0, uint32_t y0, int smp0, uint32_t x1, uint32_t y1, int smp1) {
     constexpr float off0 = 0.0f / SPP, off1 = 1.0f / SPP, off2 = 2.0f / SPP, off3 = 3.0f / SPP;
-    auto off = [&](int k) { return k == 0 ? off0 : k == 1 ? off1 : k == 2 ? off2 : off3; };
+    auto off = [&](int k) {
+        if constexpr (SPP <= 4) return k == 0 ? off0 : k == 1 ? off1 : k == 2 ? off2 : off3;
+        else return subsample_offset_wide<SPP>(k);
+    };
     const float width = (float)p.width, height = (float)p.height;
     const F2 xres = f2add(k, f2((float)x0, (float)x1), f2(off(smp0 / SPP), off(smp1 / SPP)));
     const F2 yres = f2add(k, f2((float)y0, (float)y1), f2(off(smp0 % SPP), off(smp1 % SPP)));

@@ -871,8 +871,20 @@ void rt_phased_scratch(uint32_t width, uint32_t rows, uint32_t spp, int shape, s
         case 3:
             RT_GEO(3, 1, 1, 2, 2)
             break;
-        default:
+        case 4:
             if (shape == 1) RT_GEO(4, 1, 1, 4, 4) else RT_GEO(4, 1, 1, 2, 2)
+            break;
+        case 5:
+            RT_GEO(5, 1, 1, 2, 2)
+            break;
+        case 6:
+            RT_GEO(6, 1, 1, 2, 2)
+            break;
+        case 7:
+            RT_GEO(7, 1, 1, 2, 2)
+            break;
+        default:
+            RT_GEO(8, 1, 1, 2, 2)
             break;
     }
 #undef RT_GEO
@@ -900,6 +912,15 @@ cudaError_t rt_launch_render_phased(bool diag, const RenderParams &p, cudaStream
             return launch_phased<3, 1, 1, 2, 2>(diag, p, stream);
         case 4:
             return shape == 1 ? launch_phased<4, 1, 1, 4, 4>(diag, p, stream) : launch_phased<4, 1, 1, 2, 2>(diag, p, stream);
+        // 25 .. 64 samples per pixel: one pixel per lane, its samples in groups of four slots like the 4x4 case
+        case 5:
+            return launch_phased<5, 1, 1, 2, 2>(diag, p, stream);
+        case 6:
+            return launch_phased<6, 1, 1, 2, 2>(diag, p, stream);
+        case 7:
+            return launch_phased<7, 1, 1, 2, 2>(diag, p, stream);
+        case 8:
+            return launch_phased<8, 1, 1, 2, 2>(diag, p, stream);
         default:
             return cudaErrorInvalidValue;
     }

@@ -32,7 +32,9 @@ def assert_same(gpu, ref, what=""):
 
 
 @pytest.mark.parametrize("w,h,spp,level", [(64, 128, 2, 8), (160, 120, 1, 8), (160, 120, 3, 8), (200, 150, 4, 5),
-                                          (97, 61, 2, 9), (256, 144, 1, 10), (33, 7, 1, 8), (1, 1, 1, 8), (8, 4, 5, 2)])
+                                          (97, 61, 2, 9), (256, 144, 1, 10), (33, 7, 1, 8), (1, 1, 1, 8), (8, 4, 5, 2),
+                                          (320, 180, 5, 7), (200, 120, 6, 8), (131, 77, 7, 6), (256, 144, 8, 8),
+                                          (40, 30, 9, 5)])   # 5 .. 8: PHASED's widest templates; 9: per-lane walk only
 def test_frame_matches_oracle(rt, oracle, w, h, spp, level):
     gs, os_ = rt.Scene(level=level), oracle.Scene(level=level)
     ref, ctr = os_.render(w, h, spp)
@@ -450,9 +452,11 @@ def test_variant_used_reports_the_fallbacks(rt, gpu_scene8):
             return rt.Renderer.render(rt.RenderOptions(w, h, spp), scene, camera=camera, want_stats=True)[1].variant_used
         finally:
             rt.set_variant(rt.VARIANT_AUTO)
-    assert used(gpu_scene8, 2560, 1440, 1) in (rt.VARIANT_PHASED)
+    assert used(gpu_scene8, 2560, 1440, 1) == rt.VARIANT_PHASED
     assert used(gpu_scene8, 640, 360, 2) in (rt.VARIANT_TILE, rt.VARIANT_PHASED)
     assert used(gpu_scene8, 64, 64, 9, rt.VARIANT_PHASED) == rt.VARIANT_LANE          # spp beyond the fast path
+    assert used(gpu_scene8, 1280, 720, 5) == rt.VARIANT_PHASED and used(gpu_scene8, 960, 540, 8) == rt.VARIANT_PHASED
+    assert used(gpu_scene8, 64, 64, 6, rt.VARIANT_TILE) == rt.VARIANT_LANE            # the fused TILE kernel stops at 4x4
     assert used(gpu_scene8, 64, 64, 1, rt.VARIANT_WARP) == rt.VARIANT_WARP
     inside = rt.Scene(level=6, eye=(0.1, -0.2, -1.6))
     assert used(inside, 1280, 720, 1, rt.VARIANT_PHASED) == rt.VARIANT_LANE
