@@ -369,19 +369,25 @@ class Job:
         return gsum, g
 
 
-def roofline_block(job, workload, width, height, spp, level, rays_per_launch, ms_per_step, fb_bytes):
+def roofline_block(job, workload, width, height, spp, level, rays_per_launch, ms_per_step, fb_bytes, frames=None):
     """Hardware view first: executed FP32 flops per frame (from the committed ncu capture of THIS workload, used
     only if it was taken from the same kernel sources) / live time / live FFMA peak.  SURVEY 8(d)'s reference-work
-    figure travels beside it under its own name."""
+    figure travels beside it under its own name.  frames: the orbit frames the timed steps rendered (c5)."""
     peak_tf, peak_src = job.fp32_peak()
     fpr, fpr_src = flop_per_ray(width, height, spp, level)
     ref_tf = rays_per_launch * fpr / (ms_per_step * 1e-3) / 1e12
     cap, note = None, "no ncu capture of this workload in profiles/latest_summary.json"
     try:
         summ = json.load(open(os.path.join(ROOT, "profiles", "latest_summary.json")))
-        c = summ.get("workloads", {}).get(workload if workload != "c5" else "c3")
+        c = summ.get("workloads", {}).get(workload)
         if c and summ.get("kernel_source_hash") == kernel_source_hash():
-            cap, note = c, None
+            cap, note = dict(c), None
+            if "fp32_flop_per_orbit_frame" in c:   # c5: mean over the orbit frames this run timed
+                tab, fr = c["fp32_flop_per_orbit_frame"], (frames or [0])
+                cap["fp32_flop_per_frame"] = sum(tab[f % len(tab)] for f in fr) / len(fr)
+                wtab = c.get("warp_instructions_per_orbit_frame")
+                if wtab:
+                    cap["warp_instructions_per_frame"] = sum(wtab[f % len(wtab)] for f in fr) / len(fr)
         elif c:
             note = "the committed capture (%s) was taken from other kernel sources: not used" % summ.get("kernel_source_hash")
     except Exception:
@@ -395,9 +401,10 @@ def roofline_block(job, workload, width, height, spp, level, rays_per_launch, ms
             "executed": {k: cap[k] for k in ("fp32_flop_per_frame", "warp_instructions_per_frame", "fma_pipe_active_pct",
                                              "issue_active_pct", "dominant_kernel", "dominant_kernel_share", "source")
                          if k in cap},
-            "note": "achieved = FP32 flops the kernels EXECUTE per frame (ncu thread-level FADD+FMUL+2*FFMA counts of this "
-                    "workload, committed capture of the same sources; the work is deterministic) / live event time; "
-                    "traffic = DRAM bytes per frame of the same capture (cold L2: ncu flushes it between replays)"})
+            "note": "achieved = FP32 flops the kernels EXECUTE per frame (ncu thread-level FADD + FMUL + 2 FFMA counts of this "
+                    "workload, committed capture of the same kernel sources; the work is deterministic) / live event time; "
+                    "traffic = DRAM bytes per frame of the same capture (cold L2: ncu flushes it between replays); "
+                    "fma_pipe_active_pct = ncu's own FMA-pipe utilisation over the frame's elapsed cycles"})
     else:
         out.update({"achieved": None, "frac": None, "traffic": None, "executed": None, "note": note})
     out["reference_work"] = {
@@ -486,7 +493,8 @@ def measure_frames(job, workload, steps, warmup, cpu_baseline=False):
             "variant": job.args.variant, "variant_used": variant_used,
             "wall_ms_per_step_incl_flush": wall_ms / steps, "host_cpus": job.cpu_note,
         },
-        "roofline": roofline_block(job, workload, width, height, spp, level, rays_job / world, ms_per_step, width * height * 4),
+        "roofline": roofline_block(job, workload, width, height, spp, level, rays_job / world, ms_per_step, width * height * 4,
+                                   frames=[frame_of(i) for i in range(steps)] if sweep else None),
         "e2e": {"value": e2e_rays_job / (e2e_step * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 512,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_step,
                 "pcie": {"achieved_gbs": d2h * world / (e2e_step * 1e-3) / 1e9, "ceiling_gbs": pcie_sum,
@@ -603,20 +611,41 @@ def measure_bands(job, workload, steps, warmup, gather="peer"):
         got.close()
     job.barrier()
 
-    # ---- e2e: one shared pinned host frame, every rank copies its own blocks into it ----
-    host = SharedHostFrame(job, height * row_bytes, workload)
-    whole, tail = my_rows // block, my_rows % block
-    blk, pitch, off = block * row_bytes, row_stride * row_bytes, row_start * row_bytes
+    # ---- e2e: one shared pinned host frame (RGB8, the body of the P6 file), every rank copies its own blocks into it ----
+    # The rank's blocks go in `chunks` groups: group c is rendered on the launch stream while group c-1 is packed to
+    # RGB8 on the device (the sink drops alpha, render.rs:389-397) and copied out on a second stream.
+    rgb_row = width * 3
+    host = SharedHostFrame(job, height * rgb_row, workload)
+    own_rgb = torch.zeros((height, width, 3), dtype=torch.uint8, device="cuda")
+    copy_stream = torch.cuda.Stream()
+    n_blocks = (my_rows + block - 1) // block
+    chunks = max(1, min(job.args.band_chunks, n_blocks))
+    groups = []   # (first image row, blocks, rows) of each group of this rank's blocks
+    for c in range(chunks):
+        b0, b1 = c * n_blocks // chunks, (c + 1) * n_blocks // chunks
+        if b1 > b0:
+            first = row_start + b0 * row_stride
+            rows = sum(min(block, height - (row_start + b * row_stride)) for b in range(b0, b1))
+            groups.append((first, b1 - b0, rows))
+    done_events = [torch.cuda.Event() for _ in groups]
 
     def e2e_step(i):
-        rt.Renderer.render_row_blocks(opts, scene, row_start, row_stride, row_block, my_rows, own.data_ptr(),
-                                      pitch=row_bytes, absolute_rows=True, stream=job.stream.cuda_stream)
-        if whole:
-            rt.memcpy2d_async(host.ptr + off, pitch, own.data_ptr() + off, pitch, blk, whole, job.stream.cuda_stream)
-        if tail:
-            rt.memcpy2d_async(host.ptr + off + whole * pitch, pitch, own.data_ptr() + off + whole * pitch, pitch,
-                              tail * row_bytes, 1, job.stream.cuda_stream)
-        job.barrier()          # the frame is complete in host memory on every rank's view
+        for (first, nb, rows), ev in zip(groups, done_events):
+            rt.Renderer.render_row_blocks(opts, scene, first, row_stride, row_block, rows, own.data_ptr(),
+                                          pitch=row_bytes, absolute_rows=True, stream=job.stream.cuda_stream)
+            ev.record(job.stream)
+            copy_stream.wait_event(ev)
+            cs = copy_stream.cuda_stream
+            last = first + (nb - 1) * row_stride
+            rt.pack_rgb_rows(own.data_ptr(), own_rgb.data_ptr(), width, min(height, last + block), first, row_stride, block, cs)
+            whole = nb if last + block <= height else nb - 1
+            off, pitch = first * rgb_row, row_stride * rgb_row
+            if whole:
+                rt.memcpy2d_async(host.ptr + off, pitch, own_rgb.data_ptr() + off, pitch, block * rgb_row, whole, cs)
+            if whole < nb:   # the image's partial last block
+                rt.memcpy2d_async(host.ptr + last * rgb_row, pitch, own_rgb.data_ptr() + last * rgb_row, pitch,
+                                  (height - last) * rgb_row, 1, cs)
+        job.barrier()          # every rank's copies have landed: the frame is complete in host memory
         if rank == 0:
             _ = int(host.array[0]) + int(host.array[-1])   # the sink touches the frame
         if world > 1:
@@ -632,9 +661,9 @@ def measure_bands(job, workload, steps, warmup, gather="peer"):
     e2e_ms = (time.perf_counter() - e0) * 1e3
     job.windows.append((t_begin, time.time()))
     e2e_verified = None
-    if rank == 0 and case:
-        e2e_verified = hashlib.sha256(host.array.tobytes()).hexdigest() == case["rgba_sha256"]
-    my_bytes = my_rows * row_bytes
+    if rank == 0 and case:   # the oracle's committed hash of the P6 file of this configuration
+        e2e_verified = hashlib.sha256(b"P6\n%d %d\n255\n" % (width, height) + host.array.tobytes()).hexdigest() == case["ppm_sha256"]
+    my_bytes = my_rows * rgb_row
     pcie_sum, pcie_own = job.pcie(max(my_bytes, 1 << 20))
     host.close()
     if rank == 0:
@@ -662,13 +691,15 @@ def measure_bands(job, workload, steps, warmup, gather="peer"):
             "wall_ms_per_step_incl_flush": wall_ms / steps,
         },
         "e2e": {"value": rays_frame / (e2e_step_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 512,
-                "d2h_bytes_per_step": height * row_bytes, "steps": e2e_steps, "ms_per_step": e2e_step_ms,
-                "gathered_frame_verified": e2e_verified,
-                "pcie": {"achieved_gbs": height * row_bytes / (e2e_step_ms * 1e-3) / 1e9, "ceiling_gbs": pcie_sum,
-                         "frac": height * row_bytes / (e2e_step_ms * 1e-3) / 1e9 / pcie_sum, "rank0_alone_gbs": pcie_own},
-                "note": "per frame: every rank renders its row blocks and copies them into ONE shared pinned host frame "
-                        "(POSIX shm, cudaHostRegister in every rank) over its own PCIe link; barrier; rank 0 reads the frame; "
-                        "barrier.  ms_per_step is the latency of one gathered frame in host memory"},
+                "d2h_bytes_per_step": height * rgb_row, "steps": e2e_steps, "ms_per_step": e2e_step_ms,
+                "gathered_frame_verified": e2e_verified, "chunks": len(groups),
+                "pcie": {"achieved_gbs": height * rgb_row / (e2e_step_ms * 1e-3) / 1e9, "ceiling_gbs": pcie_sum,
+                         "frac": height * rgb_row / (e2e_step_ms * 1e-3) / 1e9 / pcie_sum, "rank0_alone_gbs": pcie_own},
+                "note": "per frame: every rank renders its row blocks in `chunks` groups, packs each group to RGB8 on the device and "
+                        "copies it into ONE shared pinned host frame (POSIX shm, cudaHostRegister in every rank; the body of the "
+                        "P6 file) over its own PCIe link while the next group renders; barrier; rank 0 reads the frame; barrier.  "
+                        "ms_per_step is the latency of one gathered frame in host memory; verified = sha256 of the P6 file == "
+                        "the oracle's"},
         "gpu_launches": steps * world * launches_per_step,
         "gathered_frame_verified": verified,
         "gathered_frame_check": "sha256 of rank 0's device frame == the oracle's committed hash for this configuration",
@@ -689,6 +720,8 @@ def main():
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="bands: 'peer' = kernels store into rank 0's frame through CUDA-IPC peer memory over NVLink; "
                          "'nccl' = dist.gather of the bands")
+    ap.add_argument("--band-chunks", type=int, default=4,
+                    help="bands e2e: groups a rank's row blocks are rendered / copied out in (copy of one overlaps the next's render)")
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-l2-flush", action="store_true")

@@ -1266,6 +1266,17 @@ int rt_memcpy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, 
     return RT_OK;
 }
 
+int rt_pack_rgb_rows(const uint8_t *rgba_frame, uint8_t *rgb_frame, uint32_t width, uint32_t height, uint32_t row_start,
+                     uint32_t row_stride, uint32_t row_block, void *stream) {
+    if (!rgba_frame || !rgb_frame) return fail(RT_ERR_INVALID, "NULL argument");
+    if (row_block == 0 || row_stride < row_block) return fail(RT_ERR_INVALID, "row_stride %u is smaller than the row block %u", row_stride, row_block);
+    if (((uint64_t)row_start * width) % 4 || ((uint64_t)row_stride * width) % 4)
+        return fail(RT_ERR_INVALID, "row blocks must start at multiples of 4 pixels (row_start %u, row_stride %u, width %u)", row_start, row_stride, width);
+    if ((((uintptr_t)rgba_frame) & 15) || (((uintptr_t)rgb_frame) & 3)) return fail(RT_ERR_INVALID, "buffers must be 16- / 4-byte aligned");
+    CUDA_TRY(rt_launch_pack_rgb_blocks(rgba_frame, rgb_frame, width, height, row_start, row_stride, row_block, (cudaStream_t)stream));
+    return RT_OK;
+}
+
 int rt_host_register(void *p, size_t bytes) {
     if (!p || !bytes) return fail(RT_ERR_INVALID, "NULL argument");
     if (rt_device_count() == 0) return fail(RT_ERR_CUDA, "no CUDA device");

@@ -221,6 +221,29 @@ __global__ void pack_rgb_kernel(const uint32_t *__restrict__ rgba, uint32_t *__r
     }
 }
 
+// The same for the row blocks one GPU owns of a frame-shaped buffer: blocks of `block_rows` rows starting at row
+// first + k * stride (k = blockIdx.y), packed to the same rows of a frame-shaped RGB8 buffer.  Block starts are
+// multiples of 4 pixels (the host checks it), so quads never straddle a block.
+__global__ void pack_rgb_blocks_kernel(const uint8_t *__restrict__ rgba, uint8_t *__restrict__ rgb, uint32_t width,
+                                       uint32_t height, uint32_t first, uint32_t stride, uint32_t block_rows) {
+    const uint32_t row0 = first + blockIdx.y * stride;
+    if (row0 >= height) return;
+    const uint32_t rows = min(block_rows, height - row0);
+    const size_t px0 = (size_t)row0 * width, n_px = (size_t)rows * width, n_quads = n_px / 4;
+    const uint4 *src = reinterpret_cast<const uint4 *>(rgba + px0 * 4);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(rgb + px0 * 3);
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_quads; q += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = src[q];
+        const uint32_t a = v.x & 0xffffffu, b = v.y & 0xffffffu, c = v.z & 0xffffffu, d = v.w & 0xffffffu;
+        dst[3 * q + 0] = a | (b << 24);
+        dst[3 * q + 1] = (b >> 8) | (c << 16);
+        dst[3 * q + 2] = (c >> 16) | (d << 8);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)  // up to 3 trailing pixels of the block
+        for (size_t px = n_quads * 4; px < n_px; px++)
+            for (int k = 0; k < 3; k++) rgb[(px0 + px) * 3 + k] = rgba[(px0 + px) * 4 + k];
+}
+
 // Register-resident FP32 chains: the live roofline denominator.
 // mode 0: FFMA; mode 1: alternating FMUL / FADD (the unfused mix the parity rule forces);
 // mode 2: packed FFMA2 (sm_100 f32x2); mode 3: packed FMUL2 / FADD2.
@@ -317,6 +340,17 @@ cudaError_t rt_launch_pack_rgb(const uint8_t *rgba, uint8_t *rgb, size_t n_px, c
     const unsigned blocks = (unsigned)((quads + 255) / 256);
     pack_rgb_kernel<<<blocks ? blocks : 1, 256, 0, stream>>>(reinterpret_cast<const uint32_t *>(rgba),
                                                               reinterpret_cast<uint32_t *>(rgb), quads, n_px);
+    return cudaGetLastError();
+}
+
+cudaError_t rt_launch_pack_rgb_blocks(const uint8_t *rgba, uint8_t *rgb, uint32_t width, uint32_t height, uint32_t first,
+                                      uint32_t stride, uint32_t block_rows, cudaStream_t stream) {
+    if (first >= height || width == 0 || block_rows == 0) return cudaSuccess;
+    const uint32_t n_blocks = (height - first + stride - 1) / stride;
+    const size_t quads = (size_t)block_rows * width / 4;
+    unsigned gx = (unsigned)((quads + 255) / 256);
+    if (gx > 1024) gx = 1024;
+    pack_rgb_blocks_kernel<<<dim3(gx ? gx : 1, n_blocks), 256, 0, stream>>>(rgba, rgb, width, height, first, stride, block_rows);
     return cudaGetLastError();
 }
 

@@ -15,6 +15,8 @@ cudaError_t rt_launch_render_preview(const rt::RenderParams &p, cudaStream_t str
 cudaError_t rt_launch_trace_rays(const float4 *sph, const uint32_t *skip, uint32_t n, size_t n_rays,
                                  const float *rays, float *hits, cudaStream_t stream);
 cudaError_t rt_launch_pack_rgb(const uint8_t *rgba, uint8_t *rgb, size_t n_px, cudaStream_t stream);
+cudaError_t rt_launch_pack_rgb_blocks(const uint8_t *rgba, uint8_t *rgb, uint32_t width, uint32_t height, uint32_t first,
+                                      uint32_t stride, uint32_t block_rows, cudaStream_t stream);
 cudaError_t rt_launch_fp32_peak(int mode, float *out, int blocks, int iters, cudaStream_t stream);
 
 // TILE variant (rt_tile.cu): regular pyramids, 1 <= spp <= 4, orthonormal camera basis.

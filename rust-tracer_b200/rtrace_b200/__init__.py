@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "rt_scene_counts", "rt_scene_export_nodes", "rt_flatten_pyramid_host", "rt_scene_light", "rt_scene_eye",
     "rt_scene_device", "rt_render_region", "rt_render_preview", "rt_render_rows", "rt_render_row_blocks", "rt_render_frame", "rt_render_sweep", "rt_render_sweep_rgb",
     "rt_render_frame_multi", "rt_render_sweep_multi",
-    "rt_count_rays", "rt_trace_rays", "rt_measure_fp32_peak", "rt_microbench_fp32", "rt_selftest_math", "rt_debug_phased_tiles", "rt_host_alloc", "rt_host_free", "rt_host_register", "rt_host_unregister", "rt_microbench_d2h", "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_memcpy", "rt_memcpy2d_async",
+    "rt_count_rays", "rt_trace_rays", "rt_measure_fp32_peak", "rt_microbench_fp32", "rt_selftest_math", "rt_debug_phased_tiles", "rt_host_alloc", "rt_host_free", "rt_host_register", "rt_host_unregister", "rt_microbench_d2h", "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_memcpy", "rt_memcpy2d_async", "rt_pack_rgb_rows",
 ]
 
 
@@ -112,6 +112,7 @@ def lib():
     L.rt_ipc_open.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.rt_ipc_close.argtypes = [vp]
     L.rt_memcpy.argtypes = [vp, vp, C.c_size_t]
+    L.rt_pack_rgb_rows.argtypes = [vp, vp, u32, u32, u32, u32, u32, vp]
     L.rt_memcpy2d_async.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp]
     L.rt_host_free.argtypes = [vp]
     L.rt_host_free.restype = None
@@ -463,6 +464,11 @@ def ipc_open(handle):
 
 def memcpy(dst, src, nbytes):
     _check(lib().rt_memcpy(C.c_void_p(dst), C.c_void_p(src), nbytes))
+
+
+def pack_rgb_rows(rgba_ptr, rgb_ptr, width, height, row_start, row_stride, row_block, stream=None):
+    _check(lib().rt_pack_rgb_rows(C.c_void_p(rgba_ptr), C.c_void_p(rgb_ptr), width, height, row_start, row_stride,
+                                  row_block, stream))
 
 
 def memcpy2d_async(dst, dpitch, src, spitch, width_bytes, rows, stream=None):
