@@ -361,12 +361,18 @@ class Job:
         return sum(a.elapsed_time(b) for a, b in ev), wall_ms
 
     def pcie(self, nbytes):
-        """Copy-only ceiling of the end-to-end numbers: every rank copies `nbytes` frames device -> pinned host at
-        the same time (barrier first); returns this job's aggregate GB/s and rank 0's own rate."""
+        """Copy-only ceiling of the end-to-end numbers: after a barrier every rank copies `nbytes` frames device ->
+        pinned host (a ring of three buffers, as the sweep's) at the same time.  Returns (job ceiling, rank 0's own
+        rate, fastest rank's rate) in GB/s; the ceiling is world x the SLOWEST rank's rate: every rank delivers the
+        same number of frames, so the slowest host link bounds the job (the sum of the ranks' rates would count the
+        speed-up the fast ranks see once the slow ones are the only ones left copying)."""
         self.barrier()
-        g = self.rt.microbench_d2h(nbytes, 24)
-        (gmax,), (gsum,) = self.reduce([g])
-        return gsum, g
+        g = self.rt.microbench_d2h(nbytes, 24, 3)
+        t = self.torch.tensor([g, -g], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        gmax, gmin = t[0].item(), -t[1].item()
+        return gmin * self.world, g, gmax
 
 
 def roofline_block(job, workload, width, height, spp, level, rays_per_launch, ms_per_step, fb_bytes, frames=None):
@@ -473,7 +479,7 @@ def measure_frames(job, workload, steps, warmup, cpu_baseline=False):
     e2e_ms = (time.perf_counter() - e0) * 1e3
     job.windows.append((t_begin, time.time()))
     d2h = width * height * 3
-    pcie_sum, pcie_own = job.pcie(d2h)
+    pcie_sum, pcie_own, pcie_fast = job.pcie(d2h)
 
     (dev_ms, e2e_ms, _, _), (_, _, rays_job, e2e_rays_job) = job.reduce([dev_ms, e2e_ms, float(rays_rank), float(e2e_rays_rank)])
     if rank != 0:
@@ -498,9 +504,11 @@ def measure_frames(job, workload, steps, warmup, cpu_baseline=False):
         "e2e": {"value": e2e_rays_job / (e2e_step * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 512,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_step,
                 "pcie": {"achieved_gbs": d2h * world / (e2e_step * 1e-3) / 1e9, "ceiling_gbs": pcie_sum,
-                         "frac": d2h * world / (e2e_step * 1e-3) / 1e9 / pcie_sum, "rank0_alone_gbs": pcie_own,
-                         "note": "achieved = frame bytes leaving all GPUs / e2e time; ceiling = copy-only rate with every "
-                                 "rank copying at once (rt_microbench_d2h, pinned host memory, no kernels)"},
+                         "frac": d2h * world / (e2e_step * 1e-3) / 1e9 / pcie_sum, "rank0_gbs": pcie_own,
+                         "fastest_rank_gbs": pcie_fast,
+                         "note": "achieved = frame bytes leaving all GPUs / e2e time; ceiling = world x the slowest rank's copy-only "
+                                 "rate with every rank copying at once into a ring of three pinned host buffers, as the "
+                                 "sweep does (rt_microbench_d2h, no kernels)"},
                 "note": "rt_render_sweep_rgb (what `rtrace --frames` calls): per frame the kernel-parameter blocks (camera, "
                         "options) go in and the RGB8 frame -- the body of the reference's P6 file, its sink drops alpha "
                         "(render.rs:389-397) -- comes out to pinned host memory; two frames render at a time while an "
@@ -664,7 +672,7 @@ def measure_bands(job, workload, steps, warmup, gather="peer"):
     if rank == 0 and case:   # the oracle's committed hash of the P6 file of this configuration
         e2e_verified = hashlib.sha256(b"P6\n%d %d\n255\n" % (width, height) + host.array.tobytes()).hexdigest() == case["ppm_sha256"]
     my_bytes = my_rows * rgb_row
-    pcie_sum, pcie_own = job.pcie(max(my_bytes, 1 << 20))
+    pcie_sum, pcie_own, pcie_fast = job.pcie(max(my_bytes, 1 << 20))
     host.close()
     if rank == 0:
         rt.device_free(frame_base)
@@ -694,7 +702,8 @@ def measure_bands(job, workload, steps, warmup, gather="peer"):
                 "d2h_bytes_per_step": height * rgb_row, "steps": e2e_steps, "ms_per_step": e2e_step_ms,
                 "gathered_frame_verified": e2e_verified, "chunks": len(groups),
                 "pcie": {"achieved_gbs": height * rgb_row / (e2e_step_ms * 1e-3) / 1e9, "ceiling_gbs": pcie_sum,
-                         "frac": height * rgb_row / (e2e_step_ms * 1e-3) / 1e9 / pcie_sum, "rank0_alone_gbs": pcie_own},
+                         "frac": height * rgb_row / (e2e_step_ms * 1e-3) / 1e9 / pcie_sum, "rank0_gbs": pcie_own,
+                         "fastest_rank_gbs": pcie_fast},
                 "note": "per frame: every rank renders its row blocks in `chunks` groups, packs each group to RGB8 on the device and "
                         "copies it into ONE shared pinned host frame (POSIX shm, cudaHostRegister in every rank; the body of the "
                         "P6 file) over its own PCIe link while the next group renders; barrier; rank 0 reads the frame; barrier.  "

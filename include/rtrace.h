@@ -273,10 +273,10 @@ int rt_pack_rgb_rows(const uint8_t *rgba_frame, uint8_t *rgb_frame, uint32_t wid
  * processes, one per GPU, copy their row blocks into); portable across devices. */
 int rt_host_register(void *p, size_t bytes);
 int rt_host_unregister(void *p);
-/* Diagnostics: copy-only device-to-host rate (GB/s) of the current device into pinned host memory
- * (`write_combined` != 0: cudaHostAllocWriteCombined) -- the ceiling of every end-to-end number whose frames
- * leave the GPU; `iters` copies of `bytes` back to back, CUDA events. */
-int rt_microbench_d2h(size_t bytes, int iters, int write_combined, double *gb_per_s);
+/* Diagnostics: copy-only device-to-host rate (GB/s) of the current device into pinned host memory -- the ceiling of
+ * every end-to-end number whose frames leave the GPU; `iters` copies of `bytes` back to back, rotating over
+ * `n_buffers` (1..8) host buffers as a sweep's ring of frames does, CUDA events. */
+int rt_microbench_d2h(size_t bytes, int iters, int n_buffers, double *gb_per_s);
 
 #ifdef __cplusplus
 }

@@ -1292,29 +1292,32 @@ int rt_host_unregister(void *p) {
 
 // Copy-only microbenchmark of the link the end-to-end numbers are bound by: `iters` device-to-host copies of
 // `bytes` from the current device into pinned host memory, back to back on one stream, timed with CUDA events.
-int rt_microbench_d2h(size_t bytes, int iters, int write_combined, double *gb_per_s) {
-    if (!gb_per_s || bytes == 0 || iters < 1) return fail(RT_ERR_INVALID, "bad argument");
+// The copies rotate over `n_buffers` host buffers (1..8): a sweep delivers frames into a ring of three, and a
+// destination that is rewritten at once is a different load on the host than fresh memory.
+int rt_microbench_d2h(size_t bytes, int iters, int n_buffers, double *gb_per_s) {
+    if (!gb_per_s || bytes == 0 || iters < 1 || n_buffers < 1 || n_buffers > 8) return fail(RT_ERR_INVALID, "bad argument");
     if (rt_device_count() == 0) return fail(RT_ERR_CUDA, "no CUDA device");
-    uint8_t *d = nullptr, *h = nullptr;
+    uint8_t *d = nullptr, *h[8] = {nullptr};
     cudaStream_t st = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     float ms = 0.0f;
     cudaError_t e = cudaMalloc(&d, bytes);
     if (e == cudaSuccess) e = cudaMemset(d, 0x5a, bytes);
-    if (e == cudaSuccess) e = cudaHostAlloc((void **)&h, bytes, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0));
+    for (int k = 0; k < n_buffers && e == cudaSuccess; k++) e = cudaHostAlloc((void **)&h[k], bytes, cudaHostAllocPortable);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&e0);
     if (e == cudaSuccess) e = cudaEventCreate(&e1);
-    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st);  // warm-up
+    for (int i = 0; i < n_buffers && e == cudaSuccess; i++) e = cudaMemcpyAsync(h[i], d, bytes, cudaMemcpyDeviceToHost, st);  // warm-up
     if (e == cudaSuccess) e = cudaEventRecord(e0, st);
-    for (int i = 0; i < iters && e == cudaSuccess; i++) e = cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st);
+    for (int i = 0; i < iters && e == cudaSuccess; i++) e = cudaMemcpyAsync(h[i % n_buffers], d, bytes, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaEventRecord(e1, st);
     if (e == cudaSuccess) e = cudaEventSynchronize(e1);
     if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     if (st) cudaStreamDestroy(st);
-    if (h) cudaFreeHost(h);
+    for (int k = 0; k < n_buffers; k++)
+        if (h[k]) cudaFreeHost(h[k]);
     if (d) cudaFree(d);
     if (e != cudaSuccess) return fail(RT_ERR_CUDA, "d2h microbench: %s", cudaGetErrorString(e));
     *gb_per_s = (double)bytes * iters / (ms * 1e-3) / 1e9;

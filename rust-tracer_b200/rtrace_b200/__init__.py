@@ -408,10 +408,10 @@ def microbench_fp32(device, mode):
     return t.value
 
 
-def microbench_d2h(nbytes, iters=20, write_combined=False):
-    """Copy-only device-to-host rate of the current device into pinned host memory, GB/s."""
+def microbench_d2h(nbytes, iters=24, n_buffers=3):
+    """Copy-only device-to-host rate of the current device into a ring of pinned host buffers, GB/s."""
     g = C.c_double()
-    _check(lib().rt_microbench_d2h(nbytes, iters, 1 if write_combined else 0, C.byref(g)))
+    _check(lib().rt_microbench_d2h(nbytes, iters, n_buffers, C.byref(g)))
     return g.value
 
 
