@@ -8,8 +8,9 @@ A *step* is one pass of the hot path over one frame: ray generation, primary and
 supersample averaging and RGBA8 quantisation of every pixel.
 
 Default line = BASELINE.json configs[4] ("c5"), the largest single-GPU configuration: the 120-frame orbit of
-the camera about the level-9 flake (87,381 spheres) at 3840x2160 with 4x4 samples; step i of rank r renders
-orbit frame (i*N + r) mod 120, so N ranks shard the sweep by frame (no data-path collective, weak scaling).
+the camera about the level-9 flake (87,381 spheres) at 3840x2160 with 4x4 samples; the job's K x N frames are
+spread evenly over the orbit and step i of rank r renders the (i*N + r)-th of them, so N ranks shard the sweep by
+frame (no data-path collective, weak scaling) and every N renders the same mix of cheap and expensive frames.
 Frame 0 is BASELINE configs[2] ("c3").  The same invocation also measures, as sub-records under `also`:
   c2        configs[1]: the reference's 20k-sphere scene at 3840x2160, 1 spp (the headline 4K render)
   c4        configs[3] at N=1: one 7680x4320, 4x4, level-9 frame on one GPU
@@ -73,11 +74,18 @@ def orbit_basis(frame, n_frames=ORBIT_FRAMES, eye=(0.0, 0.0, -4.0)):
     return rot(eye), rot((1, 0, 0)), (0, 1, 0), rot((0, 0, 1))
 
 
+def orbit_frame(k, total):
+    """Orbit frame of the k-th of a job's `total` frames: the job's frames are spread evenly over the 120-frame orbit
+    (frame cost varies 1.6x around it), so that runs with different step counts or GPU counts render the same mix and
+    their throughputs compare; with total = 120 it is frame k."""
+    return (k * ORBIT_FRAMES // max(total, 1)) % ORBIT_FRAMES
+
+
 def workload_name(name, level, width, height, spp):
     s = "%s: pyramid level %d (%d spheres) at %dx%d, %d spp" % (name, level, (4 ** level - 1) // 3, width, height,
                                                                spp * spp)
     if name == "c5":
-        s += ", %d-frame orbit sweep (step i on rank r = frame (i*N + r) mod %d)" % (ORBIT_FRAMES, ORBIT_FRAMES)
+        s += ", %d-frame orbit sweep (the job's steps x N frames spread evenly over the orbit; frame i*N + r on rank r)" % ORBIT_FRAMES
     return s
 
 
@@ -219,7 +227,7 @@ def cpu_frames(workload, width, height, spp, level, frames, threads):
     rays = secs = 0.0
     ctr = None
     for f in frames:
-        cam = o.make_camera(*orbit_basis(f % ORBIT_FRAMES)) if workload == "c5" else None
+        cam = o.make_camera(*orbit_basis(f % ORBIT_FRAMES)) if workload == "c5" else None   # f: an orbit frame index
         t0 = time.perf_counter()
         _, ctr = s.render_rows(width, height, spp, 0, 1, height, threads=threads, camera=cam)
         secs += time.perf_counter() - t0
@@ -234,9 +242,9 @@ def cpu_leg(workload, width, height, spp, level, budget_s=12.0):
     rays = secs = 0.0
     n, fpr = 0, None
     while n == 0 or (secs < budget_s and secs / n * (n + 1) < 2.5 * budget_s):
-        r, s, fpr = cpu_frames(workload, width, height, spp, level, [n], cores)
+        r, s, fpr = cpu_frames(workload, width, height, spp, level, [(n * 47) % ORBIT_FRAMES], cores)   # 0, 47, 94, 21, ..: spread
         rays, secs, n = rays + r, secs + s, n + 1
-    what = "orbit frame(s) 0..%d" % (n - 1) if workload == "c5" else "%d repeat(s) of the frame" % n
+    what = "orbit frame(s) %s" % [(k * 47) % ORBIT_FRAMES for k in range(n)] if workload == "c5" else "%d repeat(s) of the frame" % n
     return {"value": rays / secs / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
             "sample": "%s, whole %dx%d spp %d level %d frames, %.1f s" % (what, width, height, spp, level, secs),
             "flop_per_ray": fpr}
@@ -253,14 +261,14 @@ def run_reference(args, workload):
     t_all = time.perf_counter()
     wdone = 0
     for i in range(args.warmup):
-        cpu_frames(workload, width, height, spp, level, [i], cores)
+        cpu_frames(workload, width, height, spp, level, [orbit_frame(i, args.steps)], cores)
         wdone += 1
         if time.perf_counter() - t_all > 60.0:
             break
     rays = secs = 0.0
     done = 0
     for i in range(args.steps):
-        r, s, _ = cpu_frames(workload, width, height, spp, level, [i], cores)
+        r, s, _ = cpu_frames(workload, width, height, spp, level, [orbit_frame(i, args.steps)], cores)   # the native arm's mix
         rays, secs, done = rays + r, secs + s, done + 1
         if time.perf_counter() - t_all > 200.0:   # keep the whole run within a few minutes on any host
             break
@@ -435,22 +443,19 @@ def measure_frames(job, workload, steps, warmup, cpu_baseline=False):
     opts = rt.RenderOptions(width, height, spp)
     cams = [rt.make_camera(*orbit_basis(f)) for f in range(ORBIT_FRAMES)] if sweep else None
 
-    def frame_of(i):   # c5: step i of this rank renders orbit frame (i * world + rank) mod 120
-        return (i * world + rank) % ORBIT_FRAMES
+    def frame_of(i):   # c5: step i of this rank is frame i * world + rank of the job's steps * world frames
+        return orbit_frame(i * world + rank, steps * world)
     fb = torch.zeros((height, width, 4), dtype=torch.uint8, device="cuda")
     _, st0 = rt.Renderer.render_rows(opts, scene, out_ptr=fb.data_ptr(), stream=job.stream.cuda_stream, want_stats=True)
     launches_per_step, variant_used = int(st0.kernel_launches), int(st0.variant_used)
     e2e_steps = max(5, min(steps, 100))
     # rays of this rank's steps, counted on the device the way the reference's work is counted
     if sweep:
-        table = {f: scene.count_rays(width, height, spp, camera=cams[f])
-                 for f in sorted({frame_of(i) for i in range(max(steps, e2e_steps))})}
+        table = {f: scene.count_rays(width, height, spp, camera=cams[f]) for f in sorted({frame_of(i) for i in range(steps)})}
         primary = sum(table[frame_of(i)][0] for i in range(steps)) / steps
         shadow = sum(table[frame_of(i)][1] for i in range(steps)) / steps
-        e2e_rays_rank = sum(sum(table[frame_of(i)]) for i in range(e2e_steps)) / e2e_steps
     else:
         primary, shadow = scene.count_rays(width, height, spp)
-        e2e_rays_rank = primary + shadow
     rays_rank = primary + shadow
 
     def step(i):
@@ -462,30 +467,56 @@ def measure_frames(job, workload, steps, warmup, cpu_baseline=False):
     dev_ms, wall_ms = job.timed(steps, step)
 
     # ---- e2e: the C-ABI call a user makes, every frame delivered to HOST memory ----
+    # All ranks PULL frames from one queue (a counter in shared memory, rt_render_sweep_pull): the job is
+    # e2e_steps x world frames, and a rank whose host link is slower under load takes fewer of them.
     seen = []
 
     def on_frame(f, arr):
         seen.append(int(arr[0, 0, 0]))   # touch the host copy of every frame
 
-    def e2e_run(n):
-        rt.Renderer.render_sweep(opts, scene, n, on_frame=on_frame, rgb=True,
-                                 cameras=[cams[frame_of(i)] for i in range(n)] if sweep else None)
-    e2e_run(3)
+    queue = SharedCounter(job, workload)
+
+    def e2e_run(total):
+        queue.reset()
+        job.barrier()
+        taken = [0]
+
+        def next_frame():
+            i = rt.atomic_fetch_add_u64(queue.ptr, 1)
+            if i >= total:
+                return None
+            taken[0] += 1
+            return i, (cams[orbit_frame(i, total)] if sweep else None)
+        rt.Renderer.render_sweep_pull(opts, scene, next_frame, on_frame=on_frame, rgb=True)
+        return taken[0]
+    e2e_run(3 * world)
     job.barrier()
     t_begin = time.time()
     e0 = time.perf_counter()
-    e2e_run(e2e_steps)
+    my_frames = e2e_run(e2e_steps * world)
     job.barrier()
     e2e_ms = (time.perf_counter() - e0) * 1e3
     job.windows.append((t_begin, time.time()))
+    queue.close()
+    if sweep:   # rays of the job's e2e_steps * world frames, counted on the device
+        total = e2e_steps * world
+        if rank == 0:
+            for f in sorted({orbit_frame(i, total) for i in range(total)}):
+                if f not in table:
+                    table[f] = scene.count_rays(width, height, spp, camera=cams[f])
+        e2e_rays_job_total = sum(sum(table[orbit_frame(i, total)]) for i in range(total)) if rank == 0 else 0.0
+    else:
+        e2e_rays_job_total = float(primary + shadow) * e2e_steps * world
     d2h = width * height * 3
     pcie_sum, pcie_own, pcie_fast = job.pcie(d2h)
 
-    (dev_ms, e2e_ms, _, _), (_, _, rays_job, e2e_rays_job) = job.reduce([dev_ms, e2e_ms, float(rays_rank), float(e2e_rays_rank)])
+    (dev_ms, e2e_ms, _, fr_max), (_, _, rays_job, _) = job.reduce([dev_ms, e2e_ms, float(rays_rank), float(my_frames)])
+    (_, fr_min), _ = job.reduce([0.0, -float(my_frames)])
     if rank != 0:
         return None
     ms_per_step = dev_ms / steps
-    e2e_step = e2e_ms / e2e_steps
+    e2e_step = e2e_ms / e2e_steps          # time per `world` frames = per frame per GPU on average
+    e2e_rays_job = e2e_rays_job_total / e2e_steps
     rec = {
         "metric": METRIC, "value": rays_job / (ms_per_step * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world,
         "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -509,15 +540,47 @@ def measure_frames(job, workload, steps, warmup, cpu_baseline=False):
                          "note": "achieved = frame bytes leaving all GPUs / e2e time; ceiling = world x the slowest rank's copy-only "
                                  "rate with every rank copying at once into a ring of three pinned host buffers, as the "
                                  "sweep does (rt_microbench_d2h, no kernels)"},
-                "note": "rt_render_sweep_rgb (what `rtrace --frames` calls): per frame the kernel-parameter blocks (camera, "
-                        "options) go in and the RGB8 frame -- the body of the reference's P6 file, its sink drops alpha "
-                        "(render.rs:389-397) -- comes out to pinned host memory; two frames render at a time while an "
-                        "earlier one is copied out"},
+                "frames_per_rank": {"min": -fr_min, "max": fr_max, "job": e2e_steps * world},
+                "note": "rt_render_sweep_pull (the engine under `rtrace --frames K --gpus N`): the job's steps x N frames sit in one "
+                        "queue (a counter in shared memory) and every rank pulls the next one when its pipeline has room; per "
+                        "frame the kernel-parameter blocks (camera, options) go in and the RGB8 frame -- the body of the "
+                        "reference's P6 file, its sink drops alpha (render.rs:389-397) -- comes out to pinned host memory; two "
+                        "frames render at a time while an earlier one is copied out.  ms_per_step = job time / steps"},
         "gpu_launches": steps * world * launches_per_step,
     }
     if cpu_baseline:
         rec["cpu_baseline"] = cpu_leg(workload, width, height, spp, level)
     return rec
+
+
+class SharedCounter:
+    """A 64-bit counter in a POSIX shared-memory segment every rank maps: the frame queue of the end-to-end sweep."""
+
+    def __init__(self, job, tag):
+        import ctypes
+        self.job = job
+        self.path = "/dev/shm/rtrace_bench_%s_%s_queue" % (os.environ.get("MASTER_PORT", "0"), tag)
+        if job.rank == 0:
+            with open(self.path, "wb") as f:
+                f.write(b"\0" * 64)
+        job.barrier()
+        self.f = open(self.path, "r+b")
+        self.mm = mmap.mmap(self.f.fileno(), 64)
+        self.ptr = ctypes.addressof(ctypes.c_char.from_buffer(self.mm))
+
+    def reset(self):
+        self.job.barrier()
+        if self.job.rank == 0:
+            self.mm[:8] = b"\0" * 8
+        self.job.barrier()
+
+    def close(self):
+        self.job.barrier()
+        if self.job.rank == 0:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
 
 
 class SharedHostFrame:

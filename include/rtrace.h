@@ -199,13 +199,29 @@ int rt_render_frame_multi(rt_scene *const *scenes, int ngpu, const rt_camera *ca
                           uint32_t width, uint32_t height, uint32_t spp,
                           uint8_t *rgba_out, size_t rgba_len, rt_stats *stats);
 
+/* The same sweep with the frames PULLED instead of listed: whenever the pipeline has room for another frame the
+ * library calls `next(next_user, &camera, &use_camera)`, which fills the camera (or sets *use_camera = 0 for the
+ * reference camera; it is 1 on entry) and returns the frame's id (>= 0; handed back to `cb` as its frame argument)
+ * or -1 when there is nothing left.  This is how several GPUs (threads of one process, or
+ * one process per GPU sharing a counter in shared memory) draw frames from one queue, so that a GPU with a slower
+ * host link simply takes fewer of them -- the reference's pool takes every unit of work the same way
+ * (render.rs:273-298).  Frames are delivered in the order they were pulled; rgb != 0 delivers RGB8. */
+typedef int (*rt_next_frame_callback)(void *user, rt_camera *camera_out, int *use_camera);
+int rt_render_sweep_pull(const rt_scene *s, rt_next_frame_callback next, void *next_user,
+                         uint32_t width, uint32_t height, uint32_t spp, int rgb,
+                         rt_frame_callback cb, void *user, rt_stats *stats);
+/* fetch-and-add on a 64-bit counter in host memory (e.g. a POSIX shared-memory segment the ranks of a job map):
+ * the frame queue of a multi-process sweep.  Returns the value before the addition. */
+uint64_t rt_atomic_fetch_add_u64(void *addr, uint64_t value);
+
 /* The sweep sharded by FRAME over ngpu GPUs of this process (BASELINE configs[4]; scenes[g] is the replica
- * on its own device, all distinct): frame f is rendered by GPU f mod ngpu through that GPU's own pipelined
- * sweep (two frames in flight + copy-out, as rt_render_sweep) driven by its own host thread, and `cb` is
- * called on the CALLING thread in frame order 0, 1, 2, ... with a pinned host buffer valid until it returns.
- * rgb != 0 delivers RGB8 frames as rt_render_sweep_rgb does.  No data-path collective: frames are
- * independent.  Replaces the one pool that takes every unit of work and the bounded channel to the writer
- * (render.rs:271-307).  This is what `rtrace --frames K --gpus N` calls. */
+ * on its own device, all distinct): every GPU runs its own pipelined sweep (two frames in flight + copy-out, as
+ * rt_render_sweep) on its own host thread and takes the next frame of the list whenever its pipeline has room
+ * (dynamic: a GPU behind a slower host link takes fewer frames), and `cb` is called on the CALLING thread in
+ * frame order 0, 1, 2, ... with a pinned host buffer valid until it returns.  rgb != 0 delivers RGB8 frames as
+ * rt_render_sweep_rgb does.  No data-path collective: frames are independent.  Replaces the one pool that takes
+ * every unit of work and the bounded channel to the writer (render.rs:271-307).  This is what
+ * `rtrace --frames K --gpus N` calls. */
 int rt_render_sweep_multi(rt_scene *const *scenes, int ngpu, const rt_camera *cameras, uint32_t n_frames,
                           uint32_t width, uint32_t height, uint32_t spp, int rgb,
                           rt_frame_callback cb, void *user, rt_stats *stats);

@@ -714,21 +714,53 @@ int rt_render_preview(const rt_scene *cs, const rt_camera *camera, uint32_t widt
     return RT_OK;
 }
 
-static int sweep_locked(rt_scene *s, const rt_camera *cameras, uint32_t n_frames, uint32_t width, uint32_t height,
-                        uint32_t spp, rt_frame_callback cb, void *user, rt_stats *stats, bool rgb);
+// Where a sweep's frames come from: called when the pipeline has room for another frame; returns its id (>= 0, handed
+// back to the frame callback) and fills *cam (use_cam = false: the reference camera), or -1 when there is none left.
+struct FrameSource {
+    virtual ~FrameSource() {}
+    virtual int64_t next(rt_camera *cam, bool *use_cam) = 0;
+};
 
-static int sweep_impl(const rt_scene *cs, const rt_camera *cameras, uint32_t n_frames, uint32_t width, uint32_t height,
-                      uint32_t spp, rt_frame_callback cb, void *user, rt_stats *stats, bool rgb) {
+// cameras[0 .. n): the fixed list of rt_render_sweep
+struct ListSource : FrameSource {
+    const rt_camera *cameras;
+    uint32_t n, at = 0;
+    ListSource(const rt_camera *c, uint32_t n_) : cameras(c), n(n_) {}
+    int64_t next(rt_camera *cam, bool *use_cam) override {
+        if (at >= n) return -1;
+        *use_cam = cameras != nullptr;
+        if (cameras) *cam = cameras[at];
+        return (int64_t)at++;
+    }
+};
+
+// the caller's rt_next_frame_callback (rt_render_sweep_pull)
+struct CallbackSource : FrameSource {
+    rt_next_frame_callback fn;
+    void *user;
+    CallbackSource(rt_next_frame_callback f, void *u) : fn(f), user(u) {}
+    int64_t next(rt_camera *cam, bool *use_cam) override {
+        int use = 1;
+        const int64_t id = fn ? (int64_t)fn(user, cam, &use) : -1;
+        *use_cam = use != 0;
+        return id;
+    }
+};
+
+static int sweep_locked(rt_scene *s, FrameSource &src, uint32_t width, uint32_t height, uint32_t spp, rt_frame_callback cb,
+                        void *user, rt_stats *stats, bool rgb);
+
+static int sweep_impl(const rt_scene *cs, FrameSource &src, uint32_t width, uint32_t height, uint32_t spp,
+                      rt_frame_callback cb, void *user, rt_stats *stats, bool rgb) {
     rt_scene *s = const_cast<rt_scene *>(cs);
     int rc = check_frame_args(s, width, height, spp, 0, 1, height);
     if (rc != RT_OK) return rc;
     if (stats) memset(stats, 0, sizeof(*stats));
-    if (n_frames == 0) return RT_OK;
     DeviceGuard guard(s->device);
     if (!guard.ok) return fail(RT_ERR_CUDA, "cannot select device %d", s->device);
     std::lock_guard<std::mutex> lock(s->mu);
-    rc = sweep_locked(s, cameras, n_frames, width, height, spp, cb, user, stats, rgb);
-    if (rc != RT_OK) {  // leave no render or copy in flight on the double buffers (keeps the first error text)
+    rc = sweep_locked(s, src, width, height, spp, cb, user, stats, rgb);
+    if (rc != RT_OK) {  // leave no render or copy in flight on the ring buffers (keeps the first error text)
         if (s->own_stream) cudaStreamSynchronize(s->own_stream);
         if (s->render2) cudaStreamSynchronize(s->render2);
         if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
@@ -737,8 +769,8 @@ static int sweep_impl(const rt_scene *cs, const rt_camera *cameras, uint32_t n_f
     return rc;
 }
 
-static int sweep_locked(rt_scene *s, const rt_camera *cameras, uint32_t n_frames, uint32_t width, uint32_t height,
-                        uint32_t spp, rt_frame_callback cb, void *user, rt_stats *stats, bool rgb) {
+static int sweep_locked(rt_scene *s, FrameSource &src, uint32_t width, uint32_t height, uint32_t spp, rt_frame_callback cb,
+                        void *user, rt_stats *stats, bool rgb) {
     int rc = RT_OK;
     const double t0 = now_ms();
     const size_t row_bytes = (size_t)width * 4, frame_bytes = row_bytes * height;
@@ -780,38 +812,51 @@ static int sweep_locked(rt_scene *s, const rt_camera *cameras, uint32_t n_frames
         }
     }
     uint32_t launches = 0, used = 0;
-    for (uint64_t f = 0; f < (uint64_t)n_frames + (uint64_t)depth; f++) {
-        if (f < n_frames) {
-            const int k = (int)(f % (uint64_t)nb);
-            cudaStream_t rs = (depth == 2 && (f & 1u)) ? s->render2 : s->own_stream;  // PHASED scratch is per stream
-            rt::RenderParams p;
-            fill_params(s, cameras ? &cameras[f] : nullptr, width, height, spp, 0, 1, height, p);
-            p.out = s->sweep_dev[k];
-            p.pitch = row_bytes;
-            if (f >= (uint64_t)nb) CUDA_TRY(cudaStreamWaitEvent(rs, s->sweep_copied[k], 0));  // frame f-nb has left this buffer
-            rc = launch(s, p, false, rs);
-            if (rc != RT_OK) return rc;
-            launches += (uint32_t)launches_per_frame(p);
-            used = variant_used(p);
-            if (rgb) {  // the sink only needs RGB: pack on the device, copy 3 bytes per pixel
-                CUDA_TRY(rt_launch_pack_rgb(s->sweep_dev[k], s->sweep_rgb[k], (size_t)width * height, rs));
-                launches += 1;
+    uint64_t issued = 0, delivered = 0;  // frames put into / handed out of the ring, in this order
+    int64_t ids[rt_scene::SWEEP_RING] = {0, 0, 0};
+    bool more = true;
+    while (more || delivered < issued) {
+        if (more) {  // the ring has room (a frame is delivered below whenever `depth` are in flight): take the next frame
+            rt_camera cam;
+            bool use_cam = false;
+            const int64_t id = src.next(&cam, &use_cam);
+            if (id < 0) {
+                more = false;
+            } else {
+                const int k = (int)(issued % (uint64_t)nb);
+                ids[k] = id;
+                cudaStream_t rs = (depth == 2 && (issued & 1u)) ? s->render2 : s->own_stream;  // PHASED scratch is per stream
+                rt::RenderParams p;
+                fill_params(s, use_cam ? &cam : nullptr, width, height, spp, 0, 1, height, p);
+                p.out = s->sweep_dev[k];
+                p.pitch = row_bytes;
+                if (issued >= (uint64_t)nb) CUDA_TRY(cudaStreamWaitEvent(rs, s->sweep_copied[k], 0));  // its previous frame has left this buffer
+                rc = launch(s, p, false, rs);
+                if (rc != RT_OK) return rc;
+                launches += (uint32_t)launches_per_frame(p);
+                used = variant_used(p);
+                if (rgb) {  // the sink only needs RGB: pack on the device, copy 3 bytes per pixel
+                    CUDA_TRY(rt_launch_pack_rgb(s->sweep_dev[k], s->sweep_rgb[k], (size_t)width * height, rs));
+                    launches += 1;
+                }
+                CUDA_TRY(cudaEventRecord(s->sweep_rendered[k], rs));
+                CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->sweep_rendered[k], 0));
+                CUDA_TRY(cudaMemcpyAsync(s->sweep_host[k], rgb ? s->sweep_rgb[k] : s->sweep_dev[k], out_bytes, cudaMemcpyDeviceToHost, s->copy_stream));
+                CUDA_TRY(cudaEventRecord(s->sweep_copied[k], s->copy_stream));
+                issued++;
             }
-            CUDA_TRY(cudaEventRecord(s->sweep_rendered[k], rs));
-            CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->sweep_rendered[k], 0));
-            CUDA_TRY(cudaMemcpyAsync(s->sweep_host[k], rgb ? s->sweep_rgb[k] : s->sweep_dev[k], out_bytes, cudaMemcpyDeviceToHost, s->copy_stream));
-            CUDA_TRY(cudaEventRecord(s->sweep_copied[k], s->copy_stream));
         }
-        if (f >= (uint64_t)depth) {  // hand frame f-depth to the caller while the later ones render
-            const uint64_t done = f - (uint64_t)depth;
-            const int k = (int)(done % (uint64_t)nb);
+        if (issued - delivered > (uint64_t)depth || (!more && delivered < issued)) {
+            // hand the oldest frame to the caller while the later ones render
+            const int k = (int)(delivered % (uint64_t)nb);
             CUDA_TRY(cudaEventSynchronize(s->sweep_copied[k]));
-            if (cb) cb(user, (uint32_t)done, s->sweep_host[k], out_bytes);
+            if (cb) cb(user, (uint32_t)ids[k], s->sweep_host[k], out_bytes);
+            delivered++;
         }
     }
     if (stats) {
         stats->total_ms = now_ms() - t0;
-        stats->primary_rays = (uint64_t)width * height * spp * spp * n_frames;
+        stats->primary_rays = (uint64_t)width * height * spp * spp * issued;
         stats->kernel_launches = launches;
         stats->gpus = 1;
         stats->variant_used = used;
@@ -821,12 +866,21 @@ static int sweep_locked(rt_scene *s, const rt_camera *cameras, uint32_t n_frames
 
 int rt_render_sweep(const rt_scene *s, const rt_camera *cameras, uint32_t n_frames, uint32_t width, uint32_t height,
                     uint32_t spp, rt_frame_callback cb, void *user, rt_stats *stats) {
-    return sweep_impl(s, cameras, n_frames, width, height, spp, cb, user, stats, false);
+    ListSource src(cameras, n_frames);
+    return sweep_impl(s, src, width, height, spp, cb, user, stats, false);
 }
 
 int rt_render_sweep_rgb(const rt_scene *s, const rt_camera *cameras, uint32_t n_frames, uint32_t width, uint32_t height,
                         uint32_t spp, rt_frame_callback cb, void *user, rt_stats *stats) {
-    return sweep_impl(s, cameras, n_frames, width, height, spp, cb, user, stats, true);
+    ListSource src(cameras, n_frames);
+    return sweep_impl(s, src, width, height, spp, cb, user, stats, true);
+}
+
+int rt_render_sweep_pull(const rt_scene *s, rt_next_frame_callback next, void *next_user, uint32_t width, uint32_t height,
+                         uint32_t spp, int rgb, rt_frame_callback cb, void *user, rt_stats *stats) {
+    if (!next) return fail(RT_ERR_INVALID, "next-frame callback is NULL");
+    CallbackSource src(next, next_user);
+    return sweep_impl(s, src, width, height, spp, cb, user, stats, rgb != 0);
 }
 
 // Body of rt_render_frame_multi once every scene's scratch is locked.  `launched` records the GPUs that have
@@ -982,41 +1036,57 @@ int rt_render_frame_multi(rt_scene *const *scenes, int ngpu, const rt_camera *ca
 // ---------------------------------------------------------------------------
 // The reference has ONE scheduler that owns every unit of work and a consumer that takes the results as they
 // come (render.rs:271-307: pool.execute per bucket, sync_channel(4), the main thread draining into the
-// writer).  Here the unit is a frame: frame f goes to GPU f mod N, every GPU runs the pipelined single-GPU
-// sweep over its own frames on its own host thread (launches of the GPUs never queue behind one another), and
-// the calling thread hands the frames to `cb` in frame order -- a worker blocks in its hand-over until the
-// caller has returned from the callback, because the pinned buffer is only valid that long; that is the
-// bounded channel.
+// writer).  Here the unit is a frame and the pool is the GPUs: every GPU runs the pipelined single-GPU sweep on
+// its own host thread and PULLS the next frame of the list whenever its pipeline has room, so a GPU whose host
+// link is slower (on the 8-GPU boxes of this pool four GPUs share one uplink: 12.6 GB/s each under load against
+// 21 GB/s for the other four) simply takes fewer frames.  The calling thread hands the frames to `cb` in frame
+// order; a worker whose frame is not yet due blocks in its hand-over (its pinned buffer is only valid that long),
+// which bounds how far a fast GPU runs ahead to the depth of its ring -- the bounded channel.
 }  // extern "C"
 
 namespace {
 
-struct SweepShare {
-    // hand-over slot of one GPU's worker thread
+struct SweepBoard {
     std::mutex mu;
     std::condition_variable cv;
-    bool ready = false, consumed = false, finished = false, abort = false;
+    const rt_camera *cameras = nullptr;
+    uint32_t n_frames = 0;
+    uint32_t next_issue = 0;    // next frame of the list a worker may take
+    uint32_t next_deliver = 0;  // frame the caller hands out next
+    bool ready = false, abort = false;  // a worker offers frame `frame`; the caller gave up
     uint32_t frame = 0;
     const uint8_t *data = nullptr;
     size_t len = 0;
+    int workers_left = 0;
     int rc = RT_OK;
     char err[512] = "";
-    rt_stats stats;
-    uint32_t stride = 1, offset = 0;  // this GPU renders global frames offset, offset + stride, ...
 };
 
-void sweep_share_callback(void *user, uint32_t local_frame, const uint8_t *data, size_t len) {
-    SweepShare *sh = static_cast<SweepShare *>(user);
-    std::unique_lock<std::mutex> lock(sh->mu);
-    if (sh->abort) return;  // the caller gave up: let this GPU's pipeline run dry without hand-overs
-    sh->frame = sh->offset + local_frame * sh->stride;
-    sh->data = data;
-    sh->len = len;
-    sh->consumed = false;
-    sh->ready = true;
-    sh->cv.notify_all();
-    sh->cv.wait(lock, [&] { return sh->consumed || sh->abort; });
-    sh->ready = false;
+struct BoardSource : FrameSource {
+    SweepBoard &b;
+    explicit BoardSource(SweepBoard &board) : b(board) {}
+    int64_t next(rt_camera *cam, bool *use_cam) override {
+        std::lock_guard<std::mutex> lock(b.mu);
+        if (b.abort || b.next_issue >= b.n_frames) return -1;
+        const uint32_t f = b.next_issue++;
+        *use_cam = b.cameras != nullptr;
+        if (b.cameras) *cam = b.cameras[f];
+        return (int64_t)f;
+    }
+};
+
+// a worker's frame callback: wait for the frame's turn, offer it, wait until the caller has consumed it
+void board_offer(void *user, uint32_t frame, const uint8_t *data, size_t len) {
+    SweepBoard &b = *static_cast<SweepBoard *>(user);
+    std::unique_lock<std::mutex> lock(b.mu);
+    b.cv.wait(lock, [&] { return b.abort || b.next_deliver == frame; });
+    if (b.abort) return;  // let this GPU's pipeline run dry without hand-overs
+    b.frame = frame;
+    b.data = data;
+    b.len = len;
+    b.ready = true;
+    b.cv.notify_all();
+    b.cv.wait(lock, [&] { return b.abort || b.next_deliver != frame; });
 }
 
 }  // namespace
@@ -1032,7 +1102,10 @@ int rt_render_sweep_multi(rt_scene *const *scenes, int ngpu, const rt_camera *ca
     }
     if (stats) memset(stats, 0, sizeof(*stats));
     if (n_frames == 0) return RT_OK;
-    if (ngpu == 1) return sweep_impl(scenes[0], cameras, n_frames, width, height, spp, cb, user, stats, rgb != 0);
+    if (ngpu == 1) {
+        ListSource src(cameras, n_frames);
+        return sweep_impl(scenes[0], src, width, height, spp, cb, user, stats, rgb != 0);
+    }
     {   // distinct scenes (each worker locks its own)
         std::vector<rt_scene *> order(scenes, scenes + ngpu);
         std::sort(order.begin(), order.end());
@@ -1041,62 +1114,65 @@ int rt_render_sweep_multi(rt_scene *const *scenes, int ngpu, const rt_camera *ca
     }
     const double t0 = now_ms();
     const int variant = g_variant;  // the caller's choice travels to the workers (it is thread-local)
-    std::vector<SweepShare> share((size_t)ngpu);
-    std::vector<std::vector<rt_camera>> cams((size_t)ngpu);
+    SweepBoard board;
+    board.cameras = cameras;
+    board.n_frames = n_frames;
+    board.workers_left = ngpu;
+    std::vector<rt_stats> wstats((size_t)ngpu);
     std::vector<std::thread> workers;
     for (int g = 0; g < ngpu; g++) {
-        SweepShare &sh = share[(size_t)g];
-        sh.stride = (uint32_t)ngpu;
-        sh.offset = (uint32_t)g;
-        memset(&sh.stats, 0, sizeof(sh.stats));
-        const uint32_t mine = n_frames > (uint32_t)g ? (n_frames - (uint32_t)g + (uint32_t)ngpu - 1) / (uint32_t)ngpu : 0;
-        if (cameras)
-            for (uint32_t i = 0; i < mine; i++) cams[(size_t)g].push_back(cameras[(size_t)g + (size_t)i * ngpu]);
-        workers.emplace_back([&, g, mine, variant]() {
-            SweepShare &me = share[(size_t)g];
+        memset(&wstats[(size_t)g], 0, sizeof(rt_stats));
+        workers.emplace_back([&, g, variant]() {
             g_variant = variant;
-            int rc = RT_OK;
-            if (mine) rc = sweep_impl(scenes[g], cameras ? cams[(size_t)g].data() : nullptr, mine, width, height, spp, sweep_share_callback, &me, &me.stats, rgb != 0);
-            std::lock_guard<std::mutex> lock(me.mu);
-            me.rc = rc;
-            if (rc != RT_OK) snprintf(me.err, sizeof(me.err), "GPU %d: %s", scenes[g]->device, g_err);
-            me.finished = true;
-            me.cv.notify_all();
+            BoardSource src(board);
+            const int rc = sweep_impl(scenes[g], src, width, height, spp, board_offer, &board, &wstats[(size_t)g], rgb != 0);
+            std::lock_guard<std::mutex> lock(board.mu);
+            if (rc != RT_OK && board.rc == RT_OK) {
+                board.rc = rc;
+                snprintf(board.err, sizeof(board.err), "GPU %d: %s", scenes[g]->device, g_err);
+                board.abort = true;
+            }
+            board.workers_left--;
+            board.cv.notify_all();
         });
     }
-    int rc = RT_OK;
-    char err[512] = "";
-    for (uint32_t f = 0; f < n_frames && rc == RT_OK; f++) {
-        SweepShare &sh = share[(size_t)(f % (uint32_t)ngpu)];
-        std::unique_lock<std::mutex> lock(sh.mu);
-        sh.cv.wait(lock, [&] { return (sh.ready && sh.frame == f) || sh.finished; });
-        if (!(sh.ready && sh.frame == f)) {  // the worker ended before delivering frame f
-            rc = sh.rc != RT_OK ? sh.rc : RT_ERR_CUDA;
-            snprintf(err, sizeof(err), "%s", sh.rc != RT_OK ? sh.err : "sweep worker ended early");
-            break;
+    {
+        std::unique_lock<std::mutex> lock(board.mu);
+        for (uint32_t f = 0; f < n_frames; f++) {
+            board.cv.wait(lock, [&] { return board.abort || (board.ready && board.frame == f) || board.workers_left == 0; });
+            if (!(board.ready && board.frame == f)) {  // a worker failed, or all ended without delivering frame f
+                if (board.rc == RT_OK) {
+                    board.rc = RT_ERR_CUDA;
+                    snprintf(board.err, sizeof(board.err), "sweep workers ended before frame %u", f);
+                }
+                board.abort = true;
+                board.cv.notify_all();
+                break;
+            }
+            const uint8_t *data = board.data;
+            const size_t len = board.len;
+            lock.unlock();
+            if (cb) cb(user, f, data, len);  // on the calling thread, without the board's lock
+            lock.lock();
+            board.ready = false;
+            board.next_deliver = f + 1;
+            board.cv.notify_all();
         }
-        if (cb) cb(user, f, sh.data, sh.len);
-        sh.consumed = true;
-        sh.cv.notify_all();
     }
-    if (rc != RT_OK)
-        for (SweepShare &sh : share) {
-            std::lock_guard<std::mutex> lock(sh.mu);
-            sh.abort = true;
-            sh.cv.notify_all();
-        }
     for (std::thread &t : workers) t.join();
-    for (SweepShare &sh : share)
-        if (rc == RT_OK && sh.rc != RT_OK) rc = sh.rc, snprintf(err, sizeof(err), "%s", sh.err);
-    if (rc != RT_OK) return fail(rc, "%s", err);
+    if (board.rc != RT_OK) return fail(board.rc, "%s", board.err);
     if (stats) {
         stats->total_ms = now_ms() - t0;
         stats->primary_rays = (uint64_t)width * height * spp * spp * n_frames;
-        for (SweepShare &sh : share) stats->kernel_launches += sh.stats.kernel_launches;
+        for (const rt_stats &w : wstats) stats->kernel_launches += w.kernel_launches;
         stats->gpus = (uint32_t)ngpu;
-        stats->variant_used = share[0].stats.variant_used;
+        stats->variant_used = wstats[0].variant_used;
     }
     return RT_OK;
+}
+
+uint64_t rt_atomic_fetch_add_u64(void *addr, uint64_t value) {
+    return __atomic_fetch_add(static_cast<uint64_t *>(addr), value, __ATOMIC_SEQ_CST);
 }
 
 int rt_count_rays(const rt_scene *s, const rt_camera *camera, uint32_t width, uint32_t height, uint32_t spp,

@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "rt_scene_create", "rt_scene_create_default", "rt_scene_create_from_nodes", "rt_scene_destroy",
     "rt_scene_counts", "rt_scene_export_nodes", "rt_flatten_pyramid_host", "rt_scene_light", "rt_scene_eye",
     "rt_scene_device", "rt_render_region", "rt_render_preview", "rt_render_rows", "rt_render_row_blocks", "rt_render_frame", "rt_render_sweep", "rt_render_sweep_rgb",
-    "rt_render_frame_multi", "rt_render_sweep_multi",
+    "rt_render_frame_multi", "rt_render_sweep_multi", "rt_render_sweep_pull", "rt_atomic_fetch_add_u64",
     "rt_count_rays", "rt_trace_rays", "rt_measure_fp32_peak", "rt_microbench_fp32", "rt_selftest_math", "rt_debug_phased_tiles", "rt_host_alloc", "rt_host_free", "rt_host_register", "rt_host_unregister", "rt_microbench_d2h", "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_memcpy", "rt_memcpy2d_async", "rt_pack_rgb_rows",
 ]
 
@@ -45,6 +45,7 @@ class Stats(C.Structure):
 
 
 FRAME_CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint8), C.c_size_t)
+NEXT_FRAME_CALLBACK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(Camera), C.POINTER(C.c_int))
 
 _lib = None
 
@@ -99,6 +100,9 @@ def lib():
                                         C.POINTER(Stats)]
     L.rt_render_sweep_multi.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(Camera), u32, u32, u32, u32, C.c_int,
                                         FRAME_CALLBACK, vp, C.POINTER(Stats)]
+    L.rt_render_sweep_pull.argtypes = [vp, NEXT_FRAME_CALLBACK, vp, u32, u32, u32, C.c_int, FRAME_CALLBACK, vp, C.POINTER(Stats)]
+    L.rt_atomic_fetch_add_u64.argtypes = [vp, C.c_uint64]
+    L.rt_atomic_fetch_add_u64.restype = C.c_uint64
     L.rt_count_rays.argtypes = [vp, C.POINTER(Camera), u32, u32, u32, u32, u32, u32, u64p, u64p]
     L.rt_trace_rays.argtypes = [vp, C.c_size_t, vp, vp]
     L.rt_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -367,6 +371,31 @@ class Renderer:
         return st
 
     @staticmethod
+    def render_sweep_pull(options, scene, next_frame, on_frame=None, rgb=False):
+        """Sweep whose frames are pulled: next_frame() -> (frame_id, Camera or None = the reference camera), or
+        None when nothing is left; on_frame(frame_id, array) per delivered frame (in pull order)."""
+        w, h, spp = options.width, options.height, options.samples_per_pixel
+
+        def _next(user, cam_out, use_cam):
+            nxt = next_frame()
+            if nxt is None:
+                return -1
+            if nxt[1] is None:
+                use_cam[0] = 0
+            else:
+                C.memmove(cam_out, C.byref(nxt[1]), C.sizeof(Camera))
+            return int(nxt[0])
+
+        def _cb(user, frame, ptr, nbytes):
+            if on_frame is not None:
+                on_frame(int(frame), np.ctypeslib.as_array(ptr, shape=(h, w, 3 if rgb else 4)))
+
+        nx, cb = NEXT_FRAME_CALLBACK(_next), FRAME_CALLBACK(_cb)
+        st = Stats()
+        _check(lib().rt_render_sweep_pull(scene.handle, nx, None, w, h, spp, 1 if rgb else 0, cb, None, C.byref(st)))
+        return st
+
+    @staticmethod
     def render_sweep_multi(options, scenes, n_frames, cameras=None, on_frame=None, rgb=False):
         """The sweep sharded by frame over len(scenes) GPUs of this process (frame f on GPU f mod N);
         on_frame(f, array) is called in frame order on the calling thread."""
@@ -413,6 +442,10 @@ def microbench_d2h(nbytes, iters=24, n_buffers=3):
     g = C.c_double()
     _check(lib().rt_microbench_d2h(nbytes, iters, n_buffers, C.byref(g)))
     return g.value
+
+
+def atomic_fetch_add_u64(addr, value=1):
+    return int(lib().rt_atomic_fetch_add_u64(C.c_void_p(addr), value))
 
 
 def host_register(ptr, nbytes):

@@ -460,3 +460,32 @@ def test_variant_used_reports_the_fallbacks(rt, gpu_scene8):
     assert used(gpu_scene8, 64, 64, 1, rt.VARIANT_WARP) == rt.VARIANT_WARP
     inside = rt.Scene(level=6, eye=(0.1, -0.2, -1.6))
     assert used(inside, 1280, 720, 1, rt.VARIANT_PHASED) == rt.VARIANT_LANE
+
+
+def test_sweep_pull_draws_frames_from_a_queue(rt, oracle, gpu_scene8, oracle_scene8):
+    """rt_render_sweep_pull: the library asks for the next frame whenever its pipeline has room; ids chosen by
+    the caller come back with the frames (in pull order); a None camera is the reference camera; the shared
+    counter helper is a fetch-and-add."""
+    w, h, spp = 160, 90, 2
+    cams = {f: rt.orbit_camera(f, 40) for f in (3, 11, 27)}
+    plan = [(103, cams[3]), (7, None), (111, cams[11]), (127, cams[27]), (9, None)]
+    it = iter(plan)
+    got = []
+    st = rt.Renderer.render_sweep_pull(rt.RenderOptions(w, h, spp), gpu_scene8, lambda: next(it, None),
+                                       on_frame=lambda f, a: got.append((f, a.copy())))
+    assert [f for f, _ in got] == [p[0] for p in plan] and st.primary_rays == w * h * spp * spp * len(plan)
+    base, _ = oracle_scene8.render(w, h, spp)
+    for (fid, img), (_, cam) in zip(got, plan):
+        if cam is None:
+            assert np.array_equal(img, base)
+        else:
+            oc = oracle.Camera()
+            for k in ("eye", "right", "up", "forward"):
+                getattr(oc, k)[:] = getattr(cam, k)[:]
+            assert_same(img, oracle_scene8.render(w, h, spp, camera=oc)[0], "pulled frame %d" % fid)
+    # an empty queue renders nothing
+    st = rt.Renderer.render_sweep_pull(rt.RenderOptions(w, h, spp), gpu_scene8, lambda: None, rgb=True)
+    assert st.primary_rays == 0
+    import ctypes
+    word = ctypes.c_uint64(5)
+    assert rt.atomic_fetch_add_u64(ctypes.addressof(word), 3) == 5 and word.value == 8
