@@ -24,9 +24,13 @@ pub struct RtStats {
     pub total_ms: f64,
     pub kernel_launches: u32,
     pub gpus: u32,
+    pub variant_used: u32,
+    pub reserved: u32,
 }
 
 pub type RtFrameCallback = extern "C" fn(user: *mut c_void, frame: u32, rgba: *const u8, len: usize);
+/// Fills `camera_out` (or sets `*use_camera = 0` for the reference camera) and returns the frame id, or -1.
+pub type RtNextFrameCallback = extern "C" fn(user: *mut c_void, camera_out: *mut RtCamera, use_camera: *mut c_int) -> c_int;
 
 extern "C" {
     pub fn rt_last_error() -> *const c_char;
@@ -43,6 +47,23 @@ extern "C" {
                                  height: u32, spp: u32, rgba_out: *mut u8, rgba_len: usize, stats: *mut RtStats) -> c_int;
     pub fn rt_render_sweep(s: *const RtScene, cameras: *const RtCamera, n_frames: u32, width: u32, height: u32,
                            spp: u32, cb: RtFrameCallback, user: *mut c_void, stats: *mut RtStats) -> c_int;
+    pub fn rt_render_sweep_rgb(s: *const RtScene, cameras: *const RtCamera, n_frames: u32, width: u32, height: u32,
+                               spp: u32, cb: RtFrameCallback, user: *mut c_void, stats: *mut RtStats) -> c_int;
+    pub fn rt_render_sweep_pull(s: *const RtScene, next: RtNextFrameCallback, next_user: *mut c_void, width: u32,
+                                height: u32, spp: u32, rgb: c_int, cb: RtFrameCallback, user: *mut c_void,
+                                stats: *mut RtStats) -> c_int;
+    pub fn rt_render_sweep_multi(scenes: *const *mut RtScene, ngpu: c_int, cameras: *const RtCamera, n_frames: u32,
+                                 width: u32, height: u32, spp: u32, rgb: c_int, cb: RtFrameCallback,
+                                 user: *mut c_void, stats: *mut RtStats) -> c_int;
+    pub fn rt_render_rows(s: *const RtScene, camera: *const RtCamera, width: u32, height: u32, spp: u32,
+                          row_start: u32, row_stride: u32, row_count: u32, rgba_out: *mut u8, pitch_bytes: usize,
+                          kinds_out: *mut u8, stream: *mut c_void, stats: *mut RtStats) -> c_int;
+    pub fn rt_render_row_blocks(s: *const RtScene, camera: *const RtCamera, width: u32, height: u32, spp: u32,
+                                row_start: u32, row_stride: u32, row_block: u32, row_count: u32, rgba_out: *mut u8,
+                                pitch_bytes: usize, absolute_rows: c_int, stream: *mut c_void,
+                                stats: *mut RtStats) -> c_int;
+    pub fn rt_host_alloc(bytes: usize, out: *mut *mut c_void) -> c_int;
+    pub fn rt_host_free(p: *mut c_void);
 }
 
 pub fn last_error() -> String {

@@ -4,6 +4,22 @@
 pub mod ffi;
 
 use std::io::{self, Seek, Write};
+use std::sync::Arc;
+use std::time::{Duration, Instant};
+
+/// Stand-in for `threadpool::ThreadPool` in `Renderer::render`'s signature (render.rs:260-263): the
+/// reference sizes its CPU pool with it; here the work runs on the GPUs of the scene and the value is
+/// accepted and ignored, so that callers written against the reference keep compiling.
+pub struct ThreadPool {
+    pub threads: usize,
+}
+
+impl ThreadPool {
+    pub fn new(threads: usize) -> ThreadPool {
+        assert!(threads >= 1);
+        ThreadPool { threads }
+    }
+}
 
 #[derive(Clone, Copy)]
 pub struct RenderOptions {
@@ -104,8 +120,10 @@ impl Renderer {
         writer.write_rgba_buffer(&frame);
     }
 
-    /// The whole frame on every GPU of the scene (rows interleaved, peer stores into GPU 0's frame).
-    pub fn render(o: &RenderOptions, scene: &Scene, writer: &mut dyn RGBABufferWriter) {
+    /// The reference's signature (render.rs:260-263).  The whole frame on every GPU of the scene: interleaved
+    /// blocks of 16 rows, each GPU copying its blocks straight into the host frame.  Unlike the reference,
+    /// sizes need not be multiples of 64.
+    pub fn render(o: &RenderOptions, scene: Arc<Scene>, writer: &mut dyn RGBABufferWriter, _pool: &ThreadPool) {
         writer.begin(o.width, o.height);
         let mut frame = RGBABuffer::new(&ImageRegion { l: 0, r: o.width, b: 0, t: o.height });
         let rc = unsafe {
@@ -116,6 +134,24 @@ impl Renderer {
         assert!(rc == 0, "render: {}", ffi::last_error());
         writer.write_rgba_buffer(&frame);
     }
+
+    /// A sweep of frames (extension): frames are drawn from one queue by the scene's GPUs
+    /// (rt_render_sweep_multi) and `sink(frame, bytes)` is called in frame order on this thread;
+    /// `rgb` delivers RGB8 (the body of the P6 file).
+    pub fn render_sweep<F: FnMut(u32, &[u8])>(o: &RenderOptions, scene: &Scene, cameras: &[ffi::RtCamera], rgb: bool,
+                                              mut sink: F) {
+        extern "C" fn trampoline<F: FnMut(u32, &[u8])>(user: *mut std::os::raw::c_void, frame: u32, data: *const u8, len: usize) {
+            let sink = unsafe { &mut *(user as *mut F) };
+            sink(frame, unsafe { std::slice::from_raw_parts(data, len) });
+        }
+        let rc = unsafe {
+            ffi::rt_render_sweep_multi(scene.replicas.as_ptr(), scene.replicas.len() as i32, cameras.as_ptr(),
+                                       cameras.len() as u32, o.width as u32, o.height as u32,
+                                       o.samples_per_pixel as u32, rgb as i32, trampoline::<F>,
+                                       &mut sink as *mut F as *mut std::os::raw::c_void, std::ptr::null_mut())
+        };
+        assert!(rc == 0, "render_sweep: {}", ffi::last_error());
+    }
 }
 
 pub enum FileOrAnyWriter {
@@ -123,19 +159,21 @@ pub enum FileOrAnyWriter {
     FileWriter(io::BufWriter<std::fs::File>),
 }
 
-/// Binary PPM (P6, or P5 grey) of the RGBA frame with alpha dropped; rewritten from the start on
-/// every flush, flushed once more on drop.
+/// Binary PPM (P6, or P5 grey) of the RGBA frame with alpha dropped; a file sink rewrites the whole image
+/// when a buffer arrives and none was written yet or the last write is a second old (render.rs:426-432);
+/// flushed once more on drop (render.rs:331-335).
 pub struct PPMStdoutRGBABufferWriter<'a> {
     out: &'a mut FileOrAnyWriter,
     dims: Option<(u16, u16)>,
     image: Option<RGBABuffer>,
     rgb: bool,
     dirty: bool,
+    last_written_at: Option<Instant>,
 }
 
 impl<'a> PPMStdoutRGBABufferWriter<'a> {
     pub fn new(write_rgb: bool, out: &'a mut FileOrAnyWriter) -> Self {
-        PPMStdoutRGBABufferWriter { out, dims: None, image: None, rgb: write_rgb, dirty: false }
+        PPMStdoutRGBABufferWriter { out, dims: None, image: None, rgb: write_rgb, dirty: false, last_written_at: None }
     }
 
     fn flush_image(&mut self) {
@@ -182,7 +220,13 @@ impl<'a> RGBABufferWriter for PPMStdoutRGBABufferWriter<'a> {
             image.buf[dst..dst + w].copy_from_slice(&buffer.buf[src..src + w]);
         }
         self.dirty = true;
-        if let FileOrAnyWriter::FileWriter(_) = *self.out { self.flush_image(); }
+        // "Flush full image right away" (render.rs:426-432): a file sink, at most once per second
+        if let FileOrAnyWriter::FileWriter(_) = *self.out {
+            if self.last_written_at.map_or(true, |t| t + Duration::from_secs(1) <= Instant::now()) {
+                self.last_written_at = Some(Instant::now());
+                self.flush_image();
+            }
+        }
     }
 }
 

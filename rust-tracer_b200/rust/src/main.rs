@@ -2,7 +2,8 @@
 //! the image has no crates.io access).  UNBUILT here; ../host/main.cpp is the tested twin.
 extern crate sphere_tracer;
 
-use sphere_tracer::{FileOrAnyWriter, PPMStdoutRGBABufferWriter, RenderOptions, Renderer, Scene};
+use sphere_tracer::{FileOrAnyWriter, PPMStdoutRGBABufferWriter, RenderOptions, Renderer, Scene, ThreadPool};
+use std::sync::Arc;
 use std::{env, fs, io, path::Path, process};
 
 fn usage_error(msg: &str) -> ! {
@@ -41,7 +42,10 @@ fn main() {
         output = Some(arg);
     }
     let output_file = output.unwrap_or_else(|| usage_error("The following required arguments were not provided:\n    <output>"));
-    let _num_cores: usize = cores.parse().unwrap();
+    // main.rs:24-29,56-61: RTRACEMAXPROCS (default 1, unparsable -> 1); --num-cores <= 1 does not override it
+    let nc_from_env: usize = std::env::var("RTRACEMAXPROCS").ok().and_then(|v| v.parse().ok()).unwrap_or(1);
+    let num_cores: usize = cores.parse().unwrap();
+    let pool = ThreadPool::new(if num_cores > 1 { num_cores } else { nc_from_env });
 
     let mut out = if output_file != "-" {
         let p = Path::new(&output_file);
@@ -59,7 +63,8 @@ fn main() {
         height: height.parse().unwrap(),
         samples_per_pixel: ssp.parse().unwrap(),
     };
-    let scene = Scene::with_level(level.parse().unwrap(), gpus.parse().unwrap());
-    Renderer::render(&options, &scene, &mut PPMStdoutRGBABufferWriter::new(true, &mut out));
+    let scene = Arc::new(Scene::with_level(level.parse().unwrap(), gpus.parse().unwrap()));
+    // main.rs:84-87, same call shape as the reference
+    Renderer::render(&options, scene.clone(), &mut PPMStdoutRGBABufferWriter::new(true, &mut out), &pool);
     process::exit(0);
 }
