@@ -34,7 +34,8 @@ def assert_same(gpu, ref, what=""):
 @pytest.mark.parametrize("w,h,spp,level", [(64, 128, 2, 8), (160, 120, 1, 8), (160, 120, 3, 8), (200, 150, 4, 5),
                                           (97, 61, 2, 9), (256, 144, 1, 10), (33, 7, 1, 8), (1, 1, 1, 8), (8, 4, 5, 2),
                                           (320, 180, 5, 7), (200, 120, 6, 8), (131, 77, 7, 6), (256, 144, 8, 8),
-                                          (40, 30, 9, 5)])   # 5 .. 8: PHASED's widest templates; 9: per-lane walk only
+                                          (40, 30, 9, 5),    # 5 .. 8: PHASED's widest templates; 9: per-lane walk only
+                                          (96, 54, 1, 11), (48, 27, 2, 12)])   # levels 11 / 12: per-lane walk only
 def test_frame_matches_oracle(rt, oracle, w, h, spp, level):
     gs, os_ = rt.Scene(level=level), oracle.Scene(level=level)
     ref, ctr = os_.render(w, h, spp)

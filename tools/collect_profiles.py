@@ -1,7 +1,7 @@
 """Copy the round's GPU evidence from gpurun_out/ (scratch) into profiles/ (tracked) and build
 profiles/latest_summary.json, which bench.py's roofline block reads:
 
-    python tools/collect_profiles.py r02
+    python tools/collect_profiles.py r02 [output directory, default profiles/]
 
 Inputs (written by tools/round_profiles.sh R): R_counters_{c1,c2,c3,c4,c5,calib}.csv (ncu --metrics ... --csv launch
 lists), R_phased_{c2,c3}.ncu-rep (ncu --set full), R_launches_bench.csv, R_matrix.jsonl.
@@ -18,7 +18,11 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402  (kernel_source_hash, WORKLOADS)
 
 R = sys.argv[1] if len(sys.argv) > 1 else "r02"
-G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+# On the GPU box only gpurun_out/ travels back (<= 64 MiB): round_profiles.sh runs this there with an output
+# directory under gpurun_out/ and drops the large .ncu-rep files afterwards; the result is copied into profiles/.
+G = os.path.join(ROOT, "gpurun_out")
+P = os.path.abspath(sys.argv[2]) if len(sys.argv) > 2 else os.path.join(ROOT, "profiles")
+os.makedirs(P, exist_ok=True)
 FADD, FMUL, FFMA = ("smsp__sass_thread_inst_executed_op_%s_pred_on.sum" % k for k in ("fadd", "fmul", "ffma"))
 
 

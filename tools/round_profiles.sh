@@ -29,4 +29,9 @@ COUNT=4 SKIP=4 bash tools/prof.sh "phase_" c1 ${R}_phased_c1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${R}_launches_bench.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${R}_ncu_bench.log 2>&1
 timeout 600 python tools/gpu_matrix.py 1,3,4,0 c1,c2,c2_l9,c2_l10,c3_l9,c3_l10,c4_l9,c4_l10 > gpurun_out/${R}_matrix.jsonl 2>&1
 tail -3 gpurun_out/${R}_matrix.jsonl
-ls -la gpurun_out/${R}_*
+# summarise here (ncu is on the box), keep only what fits the 64 MiB that travel back: the JSON / CSV summaries and
+# the C3 report (for per-source-line analysis at home)
+python tools/collect_profiles.py $R gpurun_out/profiles_$R > gpurun_out/${R}_collect.log 2>&1
+tail -40 gpurun_out/${R}_collect.log
+rm -f gpurun_out/${R}_phased_c1.ncu-rep gpurun_out/${R}_phased_c2.ncu-rep gpurun_out/${R}_phased_c4.ncu-rep gpurun_out/${R}_counters_c5.csv
+du -sh gpurun_out
