@@ -1285,6 +1285,7 @@ int rt_debug_phased_tiles(const rt_scene *cs, uint32_t cap_tiles, uint32_t *n_ti
         for (int k = 0; k < 2; k++) {
             uint32_t n = 0, b = heads[k];
             if (b == 0xfffffffeu) n = 0xffffffffu;
+            else if (b == 0xfffffffdu) n = 1;  // COVERED: one leaf occludes every shadow ray of the tile
             else
                 for (int guard_n = 0; b != 0xffffffffu && b < used && guard_n < 100000; guard_n++) n += pool[b].x, b = pool[b].y;
             counts[2 * t + k] = n;
