@@ -286,14 +286,12 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
     const uint32_t tile_x0 = pt_x * G::TW, tile_j0 = pt_y * G::TH;
     const V3 eye = v3(p.eye[0], p.eye[1], p.eye[2]);
     const ONE2 one = f2s(p.one);  // 1.0f the compiler cannot see (rt_pack.cuh)
-    // one sample per pixel: the winner's distance travels with its index (8 bytes per sample, still L2-resident at 4K);
-    // supersampled frames keep 4 bytes per sample (their winners stream through HBM) and K4 recomputes the distance
-    constexpr bool WDIST = NS == 1;
-    uint32_t *winner = p.winner + (size_t)pt * S * 32 * (WDIST ? 2 : 1);
-    auto put_winner = [&](int s, uint32_t idx, float dist) {
-        if (WDIST) reinterpret_cast<uint2 *>(winner)[s * 32 + lane] = make_uint2(idx, __float_as_uint(dist));
-        else winner[s * 32 + lane] = idx;
-    };
+    // The winner's distance travels with its index: 8 bytes per sample.  At one sample per pixel they stay in L2; on
+    // supersampled frames they stream through HBM (C3: 1.06 GB written here, read once by K4 -- 25 % of the HBM rate
+    // over the two launches), which costs less than K4 recomputing the distance: measured -5.3 % on C3, -6.7 % on C4
+    // against 4-byte winners.  The path is instruction-bound, not HBM-bound.
+    uint2 *winner = reinterpret_cast<uint2 *>(p.winner) + (size_t)pt * S * 32;
+    auto put_winner = [&](int s, uint32_t idx, float dist) { winner[s * 32 + lane] = make_uint2(idx, __float_as_uint(dist)); };
 
     uint32_t bx, bj;  // first pixel of this lane's block
     slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, 0, bx, bj);
@@ -545,8 +543,7 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
     const uint32_t pt_x = blockIdx.x * CW + (uint32_t)(warp % CW), pt_y = blockIdx.y * CH + (uint32_t)(warp / CW);
     const uint32_t pt = pt_y * geo.ptiles_x + pt_x;
     const uint32_t tile_x0 = pt_x * G::TW, tile_j0 = pt_y * G::TH;
-    constexpr bool WDIST = NS == 1;  // K2 stored the winner's distance next to its index
-    const uint32_t *winner = p.winner + (size_t)pt * S * 32 * (WDIST ? 2 : 1);
+    const uint2 *winner = reinterpret_cast<const uint2 *>(p.winner) + (size_t)pt * S * 32;  // {leaf index, hit distance} per slot (K2)
     const ONE2 one = f2s(p.one);  // 1.0f the compiler cannot see (rt_pack.cuh)
 
     const V3 eye = v3(p.eye[0], p.eye[1], p.eye[2]);
@@ -610,7 +607,7 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
             if (S > GS && g0 + GS < S) {
 #pragma unroll
                 for (int i = 0; i < GS; i++)
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(winner + (size_t)(g0 + GS + i) * 32 * (WDIST ? 2 : 1) + lane * (WDIST ? 2 : 1)));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(winner + (size_t)(g0 + GS + i) * 32 + lane));
             }
 #endif
             // ---- A: hit point, normal, g and shadow origin of the group's slots (render.rs:188-199) ----
@@ -627,22 +624,12 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
                     slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s1 / NS, xs[2 * k + 1], js[2 * k + 1]);
                     const V3x2 d = slot_dir2<SPP>(one, p, xs[2 * k], image_row(p, js[2 * k]), s0 % NS, xs[2 * k + 1],
                                                   image_row(p, js[2 * k + 1]), s1 % NS);
-                    uint32_t wi0, wi1;
-                    F2 dist;
-                    if (WDIST) {
-                        const uint2 a = reinterpret_cast<const uint2 *>(winner)[s0 * 32 + lane], b = reinterpret_cast<const uint2 *>(winner)[s1 * 32 + lane];
-                        wi0 = a.x, wi1 = b.x, dist = f2(__uint_as_float(a.y), __uint_as_float(b.y));
-                    } else {
-                        wi0 = winner[s0 * 32 + lane], wi1 = winner[s1 * 32 + lane];
-                    }
+                    const uint2 a = winner[s0 * 32 + lane], b = winner[s1 * 32 + lane];
+                    const uint32_t wi0 = a.x, wi1 = b.x;
+                    F2 dist = f2(__uint_as_float(a.y), __uint_as_float(b.y));  // primitive.rs:55-72, as K2 computed it
                     const bool hit0 = wi0 != NO_HIT, hit1 = wi1 != NO_HIT;
                     const float4 w0 = __ldg(&p.sph[hit0 ? wi0 : 0u]), w1 = __ldg(&p.sph[hit1 ? wi1 : 0u]);
                     const V3x2 cen = V3x2{f2(w0.x, w1.x), f2(w0.y, w1.y), f2(w0.z, w1.z)};
-                    if (!WDIST) {  // the winner's distance again (primitive.rs:55-72), exactly as K2 computed it
-                        const F2 rad = f2(w0.w, w1.w);
-                        const V3x2 v = vsub2(one, cen, eye2);
-                        dist = primary_distance2(one, v, f2neg(vdot2(one, v, v)), f2mul(rad, rad), d);
-                    }
                     if (!hit0) dist.x = 1.0f;
                     if (!hit1) dist.y = 1.0f;
                     // primitive.rs:83 normal; render.rs:194 g; render.rs:199 shadow origin
@@ -908,7 +895,7 @@ void rt_phased_scratch(uint32_t width, uint32_t rows, uint32_t spp, int shape, s
             break;
     }
 #undef RT_GEO
-    *winner_bytes = (size_t)np * S * 32 * sizeof(uint32_t) * (spp == 1 ? 2 : 1);  // spp 1: {index, distance} per sample
+    *winner_bytes = (size_t)np * S * 32 * sizeof(uint2);  // {leaf index, hit distance} per (padded) sample
     *hdr_bytes = (size_t)nc * sizeof(uint4);
     uint64_t units = (uint64_t)nc * 384u;
     if (units < (1u << 20)) units = 1u << 20;
