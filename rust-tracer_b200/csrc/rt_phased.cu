@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
                 slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s1 / NS, x1, j1);
                 d[k] = slot_dir2<SPP>(one, p, x0, image_row(p, j0), s0 % NS, x1, image_row(p, j1), s1 % NS);
                 bd[k] = f2s(RT_INF);
-                bi[k][0] = bi[k][1] = NO_HIT;
+                bi[k][0] = bi[k][1] = 0u;  // meaningful only once bd is finite (see `test`)
             }
             if (LAZY) {  // the only pass: every warp of the block arrives here exactly once
                 stage_wait();
@@ -402,9 +402,14 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
 #pragma unroll
                 for (int k = 0; k < GP; k++) {
                     const F2 dist = primary_distance2(one, v, nvv, rr, d[k]);
-                    // primitive.rs:79 + pre-order visiting: strictly closer wins, ties -> lowest index
-                    if (dist.x < bd[k].x || (dist.x == bd[k].x && idx < bi[k][0] && bi[k][0] != NO_HIT)) bd[k].x = dist.x, bi[k][0] = idx;
-                    if (dist.y < bd[k].y || (dist.y == bd[k].y && idx < bi[k][1] && bi[k][1] != NO_HIT)) bd[k].y = dist.y, bi[k][1] = idx;
+                    // primitive.rs:79 + pre-order visiting: strictly closer wins, ties -> lowest index.  Distances are
+                    // never negative (a root below zero is a miss, and -0 cannot arise: r*r > 0 keeps the discriminant
+                    // off -0), so their bit patterns order like the values and {distance, index} compares as ONE
+                    // unsigned 64-bit key.  A miss is +inf: it never beats the initial {+inf, 0}.
+                    const unsigned long long k0 = ((unsigned long long)__float_as_uint(dist.x) << 32) | idx;
+                    const unsigned long long k1 = ((unsigned long long)__float_as_uint(dist.y) << 32) | idx;
+                    if (k0 < (((unsigned long long)__float_as_uint(bd[k].x) << 32) | bi[k][0])) bd[k].x = dist.x, bi[k][0] = idx;
+                    if (k1 < (((unsigned long long)__float_as_uint(bd[k].y) << 32) | bi[k][1])) bd[k].y = dist.y, bi[k][1] = idx;
                 }
             };
             // farthest distance the lane still has to beat (+inf while one of its slots has no hit)
@@ -440,12 +445,14 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
             for (int k = 0; k < GP; k++) {
                 const int s0 = g0 + 2 * k, s1 = s0 + 1;
                 if (s0 < S) {
-                    put_winner(s0, bi[k][0], bd[k].x);
-                    if (bi[k][0] != NO_HIT) tmin = fminf(tmin, fabsf(bd[k].x)), tmax = fmaxf(tmax, fabsf(bd[k].x));
+                    const bool hit = bd[k].x != RT_INF;
+                    put_winner(s0, hit ? bi[k][0] : NO_HIT, bd[k].x);
+                    if (hit) tmin = fminf(tmin, bd[k].x), tmax = fmaxf(tmax, bd[k].x);
                 }
                 if (s1 < S) {
-                    put_winner(s1, bi[k][1], bd[k].y);
-                    if (bi[k][1] != NO_HIT) tmin = fminf(tmin, fabsf(bd[k].y)), tmax = fmaxf(tmax, fabsf(bd[k].y));
+                    const bool hit = bd[k].y != RT_INF;
+                    put_winner(s1, hit ? bi[k][1] : NO_HIT, bd[k].y);
+                    if (hit) tmin = fminf(tmin, bd[k].y), tmax = fmaxf(tmax, bd[k].y);
                 }
             }
         }
