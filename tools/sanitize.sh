@@ -18,7 +18,7 @@ for step in (1, 3, 8, 64, 200):
 print("sanitize-case windows done")
 if os.environ.get("SAN_ONLY") == "window":
     raise SystemExit(0)
-for level, w, h, spp in ((8, 200, 120, 1), (8, 96, 64, 4), (10, 160, 90, 2), (5, 70, 33, 3)):
+for level, w, h, spp in ((8, 200, 120, 1), (8, 96, 64, 4), (10, 160, 90, 2), (5, 70, 33, 3), (7, 90, 50, 5), (6, 64, 40, 8)):
     s = rt.Scene(level=level)
     for v in (1, 2, 3, 4):
         rt.set_variant(v)
@@ -26,6 +26,8 @@ for level, w, h, spp in ((8, 200, 120, 1), (8, 96, 64, 4), (10, 160, 90, 2), (5,
         s.count_rays(w, h, spp)
     rt.set_variant(0)
     rt.Renderer.render_sweep(rt.RenderOptions(w, h, spp), s, 3)
+    it = iter([(5, rt.orbit_camera(3, 40)), (6, None), (7, rt.orbit_camera(9, 40))])
+    rt.Renderer.render_sweep_pull(rt.RenderOptions(w, h, spp), s, lambda: next(it, None), rgb=True)
 print("sanitize-case done")
 PY
 for tool in ${SAN_TOOLS:-memcheck racecheck}; do
