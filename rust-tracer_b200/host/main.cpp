@@ -10,8 +10,8 @@
 // image` keeps working; they size the reference's CPU thread pool, which no
 // longer exists -- the GPU path ignores them.
 // Additive flags: --level=L (scene depth, default 8 as at render.rs:147),
-// --gpus=N / RTRACE_GPUS (default 1: one frame = interleaved row blocks over the GPUs; a sweep = frame f on
-// GPU f mod N), --frames=K (orbit sweep; frame f goes to <stem>.f.tga, frame 0 is the reference camera), --stats (summary on stderr), --buckets (the reference's 64x64 bucket
+// --gpus=N / RTRACE_GPUS (default 1: one frame = interleaved row blocks over the GPUs; a sweep = the GPUs draw
+// frames from one queue), --frames=K (orbit sweep; frame f goes to <stem>.f.tga, frame 0 is the reference camera), --stats (summary on stderr), --buckets (the reference's 64x64 bucket
 // schedule through Renderer::render_region instead of one launch per frame).
 #include <cerrno>
 #include <chrono>
@@ -265,7 +265,7 @@ int main(int argc, char **argv) {
             return FileOrAnyWriter::file_writer(fp);
         };
         if (frames > 1 && !preview && !args.buckets) {
-            // orbit sweep: frame f on GPU f mod N, copy-out of a frame overlapping the render of the next ones;
+            // orbit sweep: the GPUs draw frames from one queue, copy-out of a frame overlapping the render of the next ones;
             // the frames come back in order (rt_render_sweep_multi)
             std::vector<rt_camera> cams;
             for (unsigned f = 0; f < frames; f++) cams.push_back(orbit_camera(f, frames));

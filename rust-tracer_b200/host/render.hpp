@@ -4,8 +4,8 @@
 //
 // The names, argument meaning and error behaviour follow src/rust/render.rs; what
 // changed is the engine underneath Renderer::render: the thread pool + bounded
-// channel of 64x64 buckets (render.rs:271-307) became one fused CUDA launch per
-// GPU and a strided gather of row bands.  The writer trait is kept as the seam
+// channel of 64x64 buckets (render.rs:271-307) became kernel launches per GPU over
+// interleaved row blocks that every GPU copies straight into the host frame.  The writer trait is kept as the seam
 // for output sinks (render.rs:20-30).
 #pragma once
 #include <chrono>
@@ -324,7 +324,7 @@ struct Renderer {
             }
     }
 
-    // A sweep of frames (extension; BASELINE configs[4]): frame f goes to GPU f mod N, every GPU pipelines its
+    // A sweep of frames (extension; BASELINE configs[4]): the scene's GPUs draw frames from one queue, every GPU pipelines its
     // own frames (copy-out of one frame overlapping the render of the next two), and `sink(f, bytes, len)` is
     // called once per frame, in frame order, on the calling thread -- the role of the reference's main thread
     // draining the channel into the writer (render.rs:301-307).  With rgb = true the frames arrive as RGB8

@@ -397,7 +397,7 @@ class Renderer:
 
     @staticmethod
     def render_sweep_multi(options, scenes, n_frames, cameras=None, on_frame=None, rgb=False):
-        """The sweep sharded by frame over len(scenes) GPUs of this process (frame f on GPU f mod N);
+        """The sweep sharded by frame over len(scenes) GPUs of this process (the GPUs draw frames from one queue);
         on_frame(f, array) is called in frame order on the calling thread."""
         w, h, spp = options.width, options.height, options.samples_per_pixel
         cams = (Camera * n_frames)(*cameras) if cameras is not None else None
