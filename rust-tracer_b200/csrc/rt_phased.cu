@@ -55,10 +55,12 @@ static constexpr uint32_t COVERED = 0xfffffffdu;
 #define RT_P_WARPS 4
 #endif
 static constexpr int P_WARPS = RT_P_WARPS;  // warps per block of the cull launches (independent warps)
-// K2 / K4 are latency-bound below ~32 resident warps per SM (ncu: 4 blocks of 100 registers -> 49 %
-// issue-active on C3; capped at 64 registers -> 8 blocks of 4 warps, a few bytes of spill, 1.2x faster).
+// K2 / K4 are latency-bound: more resident warps win until the register cap spills.  Measured on C3 (4K, 4x4):
+// 24 / 28 / 32 / 36 / 40 warps per SM = 80 / 72 / 64 / 56 / 48 registers: 1.57 / 1.44 / 1.38 / 1.35 / 1.37 ms with the
+// round-1 kernels; with K4 no longer recomputing the hit distance 36 warps are 2.9 % (C3) / 3.9 % (C4) ahead of 32
+// and neutral on the 1-spp frame.
 #ifndef RT_PHASED_WARPS_PER_SM
-#define RT_PHASED_WARPS_PER_SM 32
+#define RT_PHASED_WARPS_PER_SM 36
 #endif
 constexpr int phased_min_blocks(int warps_per_block) {
     return RT_PHASED_WARPS_PER_SM / warps_per_block > 0 ? RT_PHASED_WARPS_PER_SM / warps_per_block : 1;
@@ -291,7 +293,9 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
     // over the two launches), which costs less than K4 recomputing the distance: measured -5.3 % on C3, -6.7 % on C4
     // against 4-byte winners.  The path is instruction-bound, not HBM-bound.
     uint2 *winner = reinterpret_cast<uint2 *>(p.winner) + (size_t)pt * S * 32;
-    auto put_winner = [&](int s, uint32_t idx, float dist) { winner[s * 32 + lane] = make_uint2(idx, __float_as_uint(dist)); };
+    // streaming stores (and streaming loads in K4): the winners pass through L2 once and must not evict the scene and
+    // the candidate chunks, which every tile re-reads (measured: -1.2 % on C3)
+    auto put_winner = [&](int s, uint32_t idx, float dist) { __stcs(&winner[s * 32 + lane], make_uint2(idx, __float_as_uint(dist))); };
 
     uint32_t bx, bj;  // first pixel of this lane's block
     slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, 0, bx, bj);
@@ -631,7 +635,7 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
                     slot_pixel<PXW, PXH>(tile_x0, tile_j0, lane, s1 / NS, xs[2 * k + 1], js[2 * k + 1]);
                     const V3x2 d = slot_dir2<SPP>(one, p, xs[2 * k], image_row(p, js[2 * k]), s0 % NS, xs[2 * k + 1],
                                                   image_row(p, js[2 * k + 1]), s1 % NS);
-                    const uint2 a = winner[s0 * 32 + lane], b = winner[s1 * 32 + lane];
+                    const uint2 a = __ldcs(&winner[s0 * 32 + lane]), b = __ldcs(&winner[s1 * 32 + lane]);  // read once: streaming
                     const uint32_t wi0 = a.x, wi1 = b.x;
                     F2 dist = f2(__uint_as_float(a.y), __uint_as_float(b.y));  // primitive.rs:55-72, as K2 computed it
                     const bool hit0 = wi0 != NO_HIT, hit1 = wi1 != NO_HIT;

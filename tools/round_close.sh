@@ -1,6 +1,7 @@
 #!/bin/bash
-# Round-2 closing run on one GPU: memcheck, the round's profile capture, the default bench line and the reference arm.
+# Round-2 closing run on one GPU: the GPU test suite, memcheck, the round's profile capture, the default bench line and the reference arm.
 mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r02_pytest_1gpu.log 2>&1; tail -3 gpurun_out/r02_pytest_1gpu.log
 SAN_TOOLS=memcheck bash tools/sanitize.sh > gpurun_out/r02_sanitize.log 2>&1; tail -4 gpurun_out/r02_sanitize.log
 bash tools/round_profiles.sh r02 > gpurun_out/r02_round_profiles.log 2>&1; tail -5 gpurun_out/r02_round_profiles.log
 cp profiles/latest_summary.json /tmp/old_summary.json; cp gpurun_out/profiles_r02/latest_summary.json profiles/latest_summary.json   # so that the bench line below carries the executed-work roofline
