@@ -71,3 +71,37 @@ def test_c5_orbit_cameras_are_the_bindings_orbit_cameras():
             assert list(getattr(a, name)) == list(getattr(b, name)), (f, name)
     ref = rt.make_camera(*bench.orbit_basis(0))
     assert list(ref.eye) == [0.0, 0.0, -4.0] and list(ref.right) == [1.0, 0.0, 0.0] and list(ref.forward) == [0.0, 0.0, 1.0]
+
+
+def test_job_frames_are_spread_evenly_over_the_orbit():
+    """bench.orbit_frame: a job's frames cover the 120-frame orbit evenly whatever its size, so that runs at
+    different GPU counts render the same mix of cheap and expensive frames; 120 frames are the orbit itself."""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert [bench.orbit_frame(k, 120) for k in range(120)] == list(range(120))
+    for total in (20, 40, 80, 160):
+        frames = [bench.orbit_frame(k, total) for k in range(total)]
+        assert frames[0] == 0 and all(0 <= f < 120 for f in frames) and frames == sorted(frames)
+        # every sixth of the orbit gets its share of the job
+        for part in range(6):
+            n = sum(1 for f in frames if 20 * part <= f < 20 * (part + 1))
+            assert abs(n - total / 6) <= 1, (total, part, n)
+    assert bench.orbit_frame(0, 0) == 0
+
+
+def test_committed_profile_summary_belongs_to_the_committed_kernels():
+    """bench.py's executed-work roofline uses profiles/latest_summary.json only if it was captured from the same
+    kernel sources: the committed capture must match the committed sources, or the bench line's roofline.frac
+    would silently be null at the end of a round."""
+    sys.path.insert(0, ROOT)
+    import bench
+    summ = json.load(open(os.path.join(ROOT, "profiles", "latest_summary.json")))
+    assert summ["kernel_source_hash"] == bench.kernel_source_hash(), "re-run tools/round_close.sh after kernel changes"
+    for w in ("c2", "c3", "c4", "c5"):
+        assert w in summ["workloads"], w
+    c3 = summ["workloads"]["c3"]
+    # the packed f32x2 instructions carry most of the flops: the scalar op counters alone see a fraction of them
+    assert c3["fp32_flop_per_frame"] > 3 * c3["fp32_flop_per_frame_scalar_op_counters"]
+    assert len(summ["workloads"]["c5"]["fp32_flop_per_orbit_frame"]) == bench.ORBIT_FRAMES
+    for mode in ("mode2", "mode3"):   # calibration: the op counters are blind to FFMA2 / FMUL2 chains
+        assert summ["calibration"][mode]["counted_flop"] < 1e-3 * summ["calibration"][mode]["true_flop"]
