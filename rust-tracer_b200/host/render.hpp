@@ -18,6 +18,7 @@
 #include <unistd.h>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -243,16 +244,36 @@ class TGARGBABufferWriter : public RGBABufferWriter {
 // render.rs:138-167: one replica of the flattened scene per GPU.
 class Scene {
   public:
-    // Scene::default() generalised by `level`; replicated on devices 0..gpus-1.
+    // Scene::default() generalised by `level`; replicated on devices 0..gpus-1.  The replicas are created
+    // concurrently, one host thread per GPU: creating a CUDA context takes about a second per device, and
+    // one after the other that was 7-8 s of start-up on an 8-GPU box.
     explicit Scene(uint32_t level = 8, int gpus = 1) {
-        const float origin[3] = {0.0f, -1.0f, 0.0f}, light[3] = {-1.0f, -3.0f, 2.0f}, eye[3] = {0.0f, 0.0f, -4.0f};
-        for (int g = 0; g < gpus; g++) {
-            if (gpus > 1 || g > 0) rt_check(set_device(g), "cudaSetDevice");
-            rt_scene *s = nullptr;
-            rt_check(rt_scene_create(level, origin, 1.0f, light, eye, &s), "Scene::default");
-            replicas_.push_back(s);
+        const int n = gpus < 1 ? 1 : gpus;
+        replicas_.assign((size_t)n, nullptr);
+        std::vector<std::string> errors((size_t)n);
+        auto create = [&](int g) {
+            const float origin[3] = {0.0f, -1.0f, 0.0f}, light[3] = {-1.0f, -3.0f, 2.0f}, eye[3] = {0.0f, 0.0f, -4.0f};
+            if (n > 1 && set_device(g) != RT_OK) {
+                errors[(size_t)g] = std::string("cudaSetDevice: ") + rt_last_error();
+                return;
+            }
+            if (rt_scene_create(level, origin, 1.0f, light, eye, &replicas_[(size_t)g]) != RT_OK)
+                errors[(size_t)g] = std::string("Scene::default: ") + rt_last_error();  // (the error text is thread-local)
+        };
+        if (n == 1) {
+            create(0);
+        } else {
+            std::vector<std::thread> workers;
+            for (int g = 0; g < n; g++) workers.emplace_back(create, g);
+            for (std::thread &t : workers) t.join();
+            set_device(0);
         }
-        if (gpus > 1) set_device(0);
+        for (const std::string &e : errors)
+            if (!e.empty()) {
+                for (rt_scene *s : replicas_) rt_scene_destroy(s);
+                replicas_.clear();
+                throw Panic(e);
+            }
     }
     ~Scene() {
         for (rt_scene *s : replicas_) rt_scene_destroy(s);
