@@ -128,3 +128,24 @@ def test_every_leaf_lies_two_leaf_radii_inside_each_ancestor_bound(rt, level):
         d = np.linalg.norm(c64[anc] - c64[i], axis=1) + float(sph[i, 3])
         slack = min(slack, float((sph[anc, 3] - d).min()))
     assert slack >= 1.99 * r_min, (slack, r_min)
+
+
+def test_frame_queue_counter_is_an_atomic_fetch_add():
+    """rt_atomic_fetch_add_u64: the frame queue of a multi-process sweep (a counter in shared memory); host-only."""
+    import ctypes
+    import threading
+    import rtrace_b200 as rt
+    word = ctypes.c_uint64(0)
+    addr = ctypes.addressof(word)
+    seen = [[] for _ in range(4)]
+
+    def worker(k):
+        for _ in range(2000):
+            seen[k].append(rt.atomic_fetch_add_u64(addr, 1))
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert word.value == 8000
+    assert sorted(v for s in seen for v in s) == list(range(8000))   # every ticket handed out exactly once
