@@ -13,7 +13,7 @@ spread evenly over the orbit and step i of rank r renders the (i*N + r)-th of th
 frame (no data-path collective, weak scaling) and every N renders the same mix of cheap and expensive frames.
 Frame 0 is BASELINE configs[2] ("c3").  The same invocation also measures, as sub-records under `also`:
   c2        configs[1]: the reference's 20k-sphere scene at 3840x2160, 1 spp (the headline 4K render)
-  c4        configs[3] at N=1: one 7680x4320, 4x4, level-9 frame on one GPU
+  c4        configs[3], 8K multi-frame: 7680x4320, 4x4, level-9 frames, whole frames per rank (weak scaling)
   c4_bands  configs[3] at N>1: ONE such frame split into interleaved 16-row blocks over the N ranks (strong
             scaling); kernel-only the blocks land in rank 0's device frame through CUDA-IPC peer stores over
             NVLink, end to end every rank copies its blocks into one shared pinned host frame over its own
@@ -823,9 +823,9 @@ def main():
                     rec.pop(k, None)
                 also[name] = rec
         sub("c2", measure_frames(job, "c2", args.steps, args.warmup))
-        if world == 1:
-            sub("c4", measure_frames(job, "c4", max(3, min(args.steps, 20)), args.warmup))
-        else:
+        # 8K frames: whole frames per rank from one queue at every N ("8K multi-frame"), and at N > 1 ONE frame split
+        sub("c4", measure_frames(job, "c4", max(3, min(args.steps, 20)), args.warmup))
+        if world > 1:
             sub("c4_bands", measure_bands(job, "c4", max(3, min(args.steps, 20)), args.warmup))
     clocks = job.sampler.stop(job.windows) if job.sampler else None
     if rank == 0:
