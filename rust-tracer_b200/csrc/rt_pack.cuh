@@ -62,8 +62,27 @@ RT_DEV F2 frecip_nr2(F2 x) {
     const F2 e = f2fma(x, r, f2s(-1.0f));
     return f2fma(r, f2neg(e), r);
 }
-// vec.rs:87-95
-RT_DEV V3x2 vnormalized2(ONE2 k, V3x2 a) { return vmulf2(a, frecip_nr2(fsqrt_nr2(vdot2(k, a, a)))); }
+// fsqrt_nr2 for arguments that are never zero: the squared length of a ray direction (>= width^2) or of a hit
+// point's offset from its sphere's centre (~r^2).  Same Newton step, same bits; the x == 0 selects (two compares and
+// two selects per pair) are dropped.  A lane without a hit normalises a dummy vector whose result is discarded.
+RT_DEV F2 fsqrt_nr2_nonzero(F2 x) {
+    float y0, y1;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(x.x));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y1) : "f"(x.y));
+    const F2 y = f2(y0, y1);
+    const F2 s = f2mul(x, y);
+    const F2 h = f2mul(y, f2s(0.5f));
+    const F2 e = f2fma(f2neg(s), s, x);
+    return f2fma(e, h, s);
+}
+// vec.rs:87-95.  NONZERO: the caller knows the vector cannot be the zero vector (measured on B200: the supersampled K2 / K4
+// gain 3 % from the shorter sqrt, the one-sample-per-pixel kernels LOSE 1.7 % -- a scheduling accident of their
+// instantiation -- so those keep the guarded form; the bits are the same either way).
+template <bool NONZERO = false>
+RT_DEV V3x2 vnormalized2(ONE2 k, V3x2 a) {
+    const F2 n2 = vdot2(k, a, a);
+    return vmulf2(a, frecip_nr2(NONZERO ? fsqrt_nr2_nonzero(n2) : fsqrt_nr2(n2)));
+}
 
 // primitive.rs:55-72 for two rays against one candidate given as broadcast pairs
 // v = c - eye, nvv = -(v.v), rr = r*r.  Branch-free: a miss yields +inf.
@@ -84,6 +103,9 @@ template <int SPP>
 RT_DEV V3x2 slot_dir2(ONE2 k, const RenderParams &p, uint32_t x0, uint32_t y0, int smp0, uint32_t x1, uint32_t y1, int smp1) {
     constexpr float off0 = 0.0f / SPP, off1 = 1.0f / SPP, off2 = 2.0f / SPP, off3 = 3.0f / SPP;
     auto off = [&](int k) {
+#ifndef RT_NO_SUBOFF_TABLE
+        if constexpr (SPP >= 2) return subsample_offset_table<SPP>(k);
+#endif
         if constexpr (SPP <= 4) return k == 0 ? off0 : k == 1 ? off1 : k == 2 ? off2 : off3;
         else return subsample_offset_wide<SPP>(k);
     };
@@ -101,7 +123,7 @@ RT_DEV V3x2 slot_dir2(ONE2 k, const RenderParams &p, uint32_t x0, uint32_t y0, i
         w.z = f2add(k, f2add(k, f2mul(f2s(p.basis[2]), d.x), f2mul(f2s(p.basis[5]), d.y)), f2mul(f2s(p.basis[8]), d.z));
         d = w;
     }
-    return vnormalized2(k, d);
+    return vnormalized2<(SPP > 1)>(k, d);
 }
 
 }  // namespace rt

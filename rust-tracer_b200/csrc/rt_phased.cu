@@ -623,7 +623,12 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
 #endif
             // ---- A: hit point, normal, g and shadow origin of the group's slots (render.rs:188-199) ----
             V3x2 no[2];           // minus the shadow origins, per pair
-            F2 nuv[2][2];         // minus their coordinates in the plane perpendicular to the light, per pair and slot
+            // Minus the shadow origins' coordinates (u, v) in the plane perpendicular to the light.  Supersampled frames keep them
+            // per pair, packed over the pair's two slots (nu, nv: 6 packed instructions per pair instead of 12 scalar ones,
+            // and the pre-filter measures both slots of a pair at once: C3 -3.2 %); the one-sample-per-pixel kernels keep one
+            // (u, v) pair per slot (nuv) -- there the packed form measured 1 % slower.
+            constexpr bool UV_PER_SLOT = NS == 1;
+            F2 nuv[2][2], nu[2], nv[2];
             float g[GS];          // g = normal . light; +inf = no hit
             uint32_t pend = 0, occluded = 0;  // bit 2k+i: slot i of pair k still needs / has found an occluder
             uint32_t xs[GS], js[GS];
@@ -644,22 +649,28 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
                     if (!hit0) dist.x = 1.0f;
                     if (!hit1) dist.y = 1.0f;
                     // primitive.rs:83 normal; render.rs:194 g; render.rs:199 shadow origin
-                    const V3x2 nrm = vnormalized2(one, vadd2(one, eye2, vsub2(one, vmulf2(d, dist), cen)));
+                    const V3x2 nrm = vnormalized2<(NS > 1)>(one, vadd2(one, eye2, vsub2(one, vmulf2(d, dist), cen)));
                     const F2 gg = vdot2(one, nrm, light2);
                     const V3x2 o = vadd2(one, vadd2(one, eye2, vmulf2(d, dist)), vmulf2(nrm, f2mul(dist, f2s(sqrt_eps))));
                     no[k] = V3x2{f2neg(o.x), f2neg(o.y), f2neg(o.z)};
-                    // -(o . e1, o . e2) per slot, computed straight into the pair the pre-filter adds to a candidate
-                    nuv[k][0] = f2(fmaf(no[k].x.x, p.lframe[0], fmaf(no[k].y.x, p.lframe[1], no[k].z.x * p.lframe[2])),
-                                   fmaf(no[k].x.x, p.lframe[3], fmaf(no[k].y.x, p.lframe[4], no[k].z.x * p.lframe[5])));
-                    nuv[k][1] = f2(fmaf(no[k].x.y, p.lframe[0], fmaf(no[k].y.y, p.lframe[1], no[k].z.y * p.lframe[2])),
-                                   fmaf(no[k].x.y, p.lframe[3], fmaf(no[k].y.y, p.lframe[4], no[k].z.y * p.lframe[5])));
+                    if constexpr (UV_PER_SLOT) {
+                        // -(o . e1, o . e2) per slot, computed straight into the pair the pre-filter adds to a candidate
+                        nuv[k][0] = f2(fmaf(no[k].x.x, p.lframe[0], fmaf(no[k].y.x, p.lframe[1], no[k].z.x * p.lframe[2])),
+                                       fmaf(no[k].x.x, p.lframe[3], fmaf(no[k].y.x, p.lframe[4], no[k].z.x * p.lframe[5])));
+                        nuv[k][1] = f2(fmaf(no[k].x.y, p.lframe[0], fmaf(no[k].y.y, p.lframe[1], no[k].z.y * p.lframe[2])),
+                                       fmaf(no[k].x.y, p.lframe[3], fmaf(no[k].y.y, p.lframe[4], no[k].z.y * p.lframe[5])));
+                    } else {
+                        // -(o . e1) and -(o . e2) of the pair's two slots at once (pre-filter only, not parity arithmetic: FMA is fine)
+                        nu[k] = f2fma(no[k].x, f2s(p.lframe[0]), f2fma(no[k].y, f2s(p.lframe[1]), f2mul(no[k].z, f2s(p.lframe[2]))));
+                        nv[k] = f2fma(no[k].x, f2s(p.lframe[3]), f2fma(no[k].y, f2s(p.lframe[4]), f2mul(no[k].z, f2s(p.lframe[5]))));
+                    }
                     g[2 * k] = hit0 ? gg.x : RT_INF;
                     g[2 * k + 1] = hit1 ? gg.y : RT_INF;
                     if (hit0 && !(gg.x >= 0.0f)) pend |= 1u << (2 * k);
                     if (hit1 && !(gg.y >= 0.0f) && s1 != s0) pend |= 2u << (2 * k);
                 } else {
                     no[k] = V3x2{f2s(0.0f), f2s(0.0f), f2s(0.0f)};
-                    nuv[k][0] = nuv[k][1] = f2s(0.0f);
+                    nuv[k][0] = nuv[k][1] = nu[k] = nv[k] = f2s(0.0f);
                     g[2 * k] = g[2 * k + 1] = RT_INF;
                     xs[2 * k] = xs[2 * k + 1] = js[2 * k] = js[2 * k + 1] = 0xffffffffu;
                 }
@@ -713,7 +724,7 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
 #pragma unroll
                 for (int i = 0; i < GS; i++) {
                     if ((pend >> i) & 1u) {
-                        const F2 q = nuv[i >> 1][i & 1];
+                        const F2 q = UV_PER_SLOT ? nuv[i >> 1][i & 1] : (i & 1) ? f2(nu[i >> 1].y, nv[i >> 1].y) : f2(nu[i >> 1].x, nv[i >> 1].x);
                         ulo = fminf(ulo, -q.x), uhi = fmaxf(uhi, -q.x), vlo = fminf(vlo, -q.y), vhi = fmaxf(vhi, -q.y);
                     }
                 }
@@ -737,13 +748,24 @@ __global__ void __launch_bounds__(32 * CW * CH, phased_min_blocks(CW * CH)) phas
                         for (uint32_t wm = __ballot_sync(FULLMASK, w_ok); wm; wm &= wm - 1u) {
                             const uint32_t b = (uint32_t)__ffs((int)wm) - 1u;
                             const uint4 u = unit(3u + SU * (c0 + b));
-                            const F2 cuv = f2(__uint_as_float(u.x), __uint_as_float(u.y));
                             const float r2 = __uint_as_float(u.z);
-                            const F2 d00 = __fadd2_rn(cuv, nuv[0][0]), d01 = __fadd2_rn(cuv, nuv[0][1]);
-                            const F2 d10 = __fadd2_rn(cuv, nuv[1][0]), d11 = __fadd2_rn(cuv, nuv[1][1]);
-                            const F2 q00 = f2mul(d00, d00), q01 = f2mul(d01, d01), q10 = f2mul(d10, d10), q11 = f2mul(d11, d11);
-                            const bool h0 = ((pend & 1u) && q00.x + q00.y <= r2) || ((pend & 2u) && q01.x + q01.y <= r2);
-                            const bool h1 = ((pend & 4u) && q10.x + q10.y <= r2) || ((pend & 8u) && q11.x + q11.y <= r2);
+                            bool h0, h1;
+                            if constexpr (UV_PER_SLOT) {
+                                const F2 cuv = f2(__uint_as_float(u.x), __uint_as_float(u.y));
+                                const F2 d00 = __fadd2_rn(cuv, nuv[0][0]), d01 = __fadd2_rn(cuv, nuv[0][1]);
+                                const F2 d10 = __fadd2_rn(cuv, nuv[1][0]), d11 = __fadd2_rn(cuv, nuv[1][1]);
+                                const F2 q00 = f2mul(d00, d00), q01 = f2mul(d01, d01), q10 = f2mul(d10, d10), q11 = f2mul(d11, d11);
+                                h0 = ((pend & 1u) && q00.x + q00.y <= r2) || ((pend & 2u) && q01.x + q01.y <= r2);
+                                h1 = ((pend & 4u) && q10.x + q10.y <= r2) || ((pend & 8u) && q11.x + q11.y <= r2);
+                            } else {
+                                // squared distance from the candidate's centre to both slots of a pair at once
+                                const F2 cu = f2s(__uint_as_float(u.x)), cv = f2s(__uint_as_float(u.y));
+                                const F2 du0 = __fadd2_rn(cu, nu[0]), dv0 = __fadd2_rn(cv, nv[0]);
+                                const F2 du1 = __fadd2_rn(cu, nu[1]), dv1 = __fadd2_rn(cv, nv[1]);
+                                const F2 q0 = f2fma(dv0, dv0, f2mul(du0, du0)), q1 = f2fma(dv1, dv1, f2mul(du1, du1));
+                                h0 = ((pend & 1u) && q0.x <= r2) || ((pend & 2u) && q0.y <= r2);
+                                h1 = ((pend & 4u) && q1.x <= r2) || ((pend & 8u) && q1.y <= r2);
+                            }
                             if (h0) m0 |= 1u << b;
                             if (h1) m1 |= 1u << b;
                         }

@@ -143,10 +143,18 @@ path = os.path.join(G, "%s_counters_c5.csv" % R)
 if os.path.exists(path):
     ks = [k for k in launches(path) if "phase_" in k["kernel"]]
     n = bench.ORBIT_FRAMES
-    if len(ks) >= 4 * (n + 1):
-        ks = ks[-4 * n:]
-        per = [ks[4 * f:4 * f + 4] for f in range(n)]
-        winst = [sum(k.get("smsp__inst_executed.sum", 0.0) for k in fr) for fr in per]
+    n_cap = (len(ks) - 4) // 4                       # frames after the warm-up frame
+    stride = next((st for st in range(1, n + 1) if len(range(0, n, st)) == n_cap), None)
+    if stride:
+        ks = ks[-4 * n_cap:]
+        cap = [sum(k.get("smsp__inst_executed.sum", 0.0) for k in ks[4 * i:4 * i + 4]) for i in range(n_cap)]
+        # frames between two captured ones: linear interpolation over the orbit angle (frame 120 is frame 0 again)
+        winst = []
+        for f in range(n):
+            i, r = divmod(f, stride)
+            a, b = cap[i], cap[(i + 1) % n_cap] if (i + 1) * stride < n else cap[0]
+            span = min(stride, n - i * stride)
+            winst.append(a + (b - a) * r / span)
         c3 = summary["workloads"].get("c3", {})
         # flops of an orbit frame = its warp-instruction count x the flops per warp-instruction of frame 0 (= C3, whose
         # per-opcode counts are known): the kernels and their instruction mix are the same, only the amount of work moves
@@ -155,8 +163,11 @@ if os.path.exists(path):
             "fp32_flop_per_orbit_frame": [w_ * per_inst for w_ in winst] if per_inst else None,
             "warp_instructions_per_orbit_frame": winst,
             "fp32_flop_per_warp_instruction": per_inst,
-            "source": "profiles/%s_counters_c5.csv.gz (ncu instruction counts of the 120 orbit frames) x flops per warp-instruction "
-                      "of frame 0 (C3's per-opcode capture)" % R}
+            "captured_orbit_frames": list(range(0, n, stride)),
+            "source": "profiles/%s_counters_c5.csv.gz (ncu instruction counts of %s of the 120 orbit frames%s) x flops per "
+                      "warp-instruction of frame 0 (C3's per-opcode capture)"
+                      % (R, "all" if stride == 1 else "every %s" % {2: "second", 3: "third", 4: "fourth"}.get(stride, "%dth" % stride),
+                         "" if stride == 1 else ", linear in between")}
         subprocess.run("gzip -9 -c %s > %s" % (path, os.path.join(P, "%s_counters_c5.csv.gz" % R)), shell=True, check=False)
         for k in ("fma_pipe_active_pct", "issue_active_pct", "dominant_kernel", "dominant_kernel_share", "dram_bytes_per_frame"):
             if "c3" in summary["workloads"] and k in summary["workloads"]["c3"]:

@@ -9,9 +9,10 @@ M=smsp__sass_thread_inst_executed_op_fadd_pred_on.sum,smsp__sass_thread_inst_exe
 for c in c2 c3 c4 c1; do
   timeout 600 ncu --metrics $M --clock-control none -k regex:phase_ --csv --log-file gpurun_out/${R}_counters_$c.csv python tools/one_frame.py $c > gpurun_out/${R}_counters_$c.log 2>&1
 done
-# the 120 orbit frames of c5: flop counters only (one pass per launch)
+# the orbit frames of c5 (every C5_STRIDE-th of the 120; collect_profiles.py interpolates between them): instruction and
+# scalar-op counters only (one pass per launch)
 F=smsp__sass_thread_inst_executed_op_fadd_pred_on.sum,smsp__sass_thread_inst_executed_op_fmul_pred_on.sum,smsp__sass_thread_inst_executed_op_ffma_pred_on.sum,smsp__inst_executed.sum
-timeout 900 ncu --metrics $F --clock-control none -k regex:phase_ --csv --log-file gpurun_out/${R}_counters_c5.csv python tools/one_frame.py c5 > gpurun_out/${R}_counters_c5.log 2>&1
+timeout 900 ncu --metrics $F --clock-control none -k regex:phase_ --csv --log-file gpurun_out/${R}_counters_c5.csv python tools/one_frame.py c5 120 ${C5_STRIDE:-1} > gpurun_out/${R}_counters_c5.log 2>&1
 # calibration: the FP32 microbenchmark kernels (16 chains x iters x 256 threads x blocks; FFMA / FMUL+FADD / FFMA2 / FMUL2+FADD2)
 timeout 300 ncu --metrics $F --clock-control none -k regex:fp32_peak --csv --log-file gpurun_out/${R}_counters_calib.csv python - > gpurun_out/${R}_counters_calib.log 2>&1 <<'PY'
 import sys
