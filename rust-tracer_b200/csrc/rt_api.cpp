@@ -1129,7 +1129,7 @@ int rt_render_sweep_multi(rt_scene *const *scenes, int ngpu, const rt_camera *ca
             std::lock_guard<std::mutex> lock(board.mu);
             if (rc != RT_OK && board.rc == RT_OK) {
                 board.rc = rc;
-                snprintf(board.err, sizeof(board.err), "GPU %d: %s", scenes[g]->device, g_err);
+                snprintf(board.err, sizeof(board.err), "GPU %d: %.*s", scenes[g]->device, (int)sizeof(board.err) - 24, g_err);  // a long message is cut, never overrun
                 board.abort = true;
             }
             board.workers_left--;
