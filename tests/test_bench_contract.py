@@ -5,6 +5,8 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -105,3 +107,28 @@ def test_committed_profile_summary_belongs_to_the_committed_kernels():
     assert len(summ["workloads"]["c5"]["fp32_flop_per_orbit_frame"]) == bench.ORBIT_FRAMES
     for mode in ("mode2", "mode3"):   # calibration: the op counters are blind to FFMA2 / FMUL2 chains
         assert summ["calibration"][mode]["counted_flop"] < 1e-3 * summ["calibration"][mode]["true_flop"]
+
+
+def test_strided_orbit_captures_interpolate_over_a_closed_orbit():
+    """tools/round_profiles.sh may capture every k-th orbit frame (C5_STRIDE); tools/orbit_interp.py fills the
+    frames in between linearly, and the frame after the last one is frame 0 again."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from orbit_interp import interpolate_orbit, stride_of
+    assert stride_of(120, 120) == 1 and stride_of(120, 40) == 3 and stride_of(120, 30) == 4 and stride_of(120, 17) is None
+    cap = [100.0 + 3 * i for i in range(40)]           # frames 0, 3, ..., 117
+    full = interpolate_orbit(cap, 120, 3)
+    assert len(full) == 120 and full[0::3] == cap
+    assert full[1] == pytest.approx(101.0) and full[2] == pytest.approx(102.0)
+    # between frame 117 and frame 120 == frame 0 the values return to frame 0's
+    assert full[118] == pytest.approx(cap[-1] + (cap[0] - cap[-1]) / 3) and full[119] == pytest.approx(cap[-1] + 2 * (cap[0] - cap[-1]) / 3)
+    assert interpolate_orbit([1.0, 2.0, 3.0], 3, 1) == [1.0, 2.0, 3.0]
+    # a stride that does not divide the orbit: the last span is shorter (frames 119 -> 120 == 0)
+    cap7 = [float(f) for f in range(0, 120, 7)]
+    full7 = interpolate_orbit(cap7, 120, 7)
+    assert full7[119] == 119.0 and len(full7) == 120
+    summ = json.load(open(os.path.join(ROOT, "profiles", "latest_summary.json")))
+    c5 = summ["workloads"]["c5"]
+    cf = c5.get("captured_orbit_frames")
+    if cf:   # the committed capture: captured frames keep their own counts
+        w = c5["warp_instructions_per_orbit_frame"]
+        assert len(w) == 120 and cf[0] == 0 and all(w[f] > 0 for f in cf)

@@ -16,6 +16,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402  (kernel_source_hash, WORKLOADS)
+from orbit_interp import interpolate_orbit, stride_of  # noqa: E402
 
 R = sys.argv[1] if len(sys.argv) > 1 else "r02"
 # On the GPU box only gpurun_out/ travels back (<= 64 MiB): round_profiles.sh runs this there with an output
@@ -144,17 +145,11 @@ if os.path.exists(path):
     ks = [k for k in launches(path) if "phase_" in k["kernel"]]
     n = bench.ORBIT_FRAMES
     n_cap = (len(ks) - 4) // 4                       # frames after the warm-up frame
-    stride = next((st for st in range(1, n + 1) if len(range(0, n, st)) == n_cap), None)
+    stride = stride_of(n, n_cap)
     if stride:
         ks = ks[-4 * n_cap:]
         cap = [sum(k.get("smsp__inst_executed.sum", 0.0) for k in ks[4 * i:4 * i + 4]) for i in range(n_cap)]
-        # frames between two captured ones: linear interpolation over the orbit angle (frame 120 is frame 0 again)
-        winst = []
-        for f in range(n):
-            i, r = divmod(f, stride)
-            a, b = cap[i], cap[(i + 1) % n_cap] if (i + 1) * stride < n else cap[0]
-            span = min(stride, n - i * stride)
-            winst.append(a + (b - a) * r / span)
+        winst = interpolate_orbit(cap, n, stride)    # stride 1: the capture itself
         c3 = summary["workloads"].get("c3", {})
         # flops of an orbit frame = its warp-instruction count x the flops per warp-instruction of frame 0 (= C3, whose
         # per-opcode counts are known): the kernels and their instruction mix are the same, only the amount of work moves
